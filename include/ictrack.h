@@ -1,0 +1,163 @@
+/*
+ * ictrack.h — C ABI of libictrack.so: the B200 (sm_100a) implementation of the
+ * inverse-compositional Gauss-Newton pose-tracking path of catree/InvCompCamTrack.
+ *
+ * Convention follows the reference's only existing FFI, misc_src/triang.c as loaded by
+ * misc_src/func_util_geom.py:582-604 (plain C symbols, caller-allocated contiguous buffers,
+ * scalars by value, SoA layouts, results written in place).  One thing is added: every call
+ * returns an int status (0 = ICT_OK) and ict_last_error() returns the message, because a GPU
+ * library can fail in ways triang.c cannot.  There is NO CPU fallback behind these symbols:
+ * without a CUDA device every compute entry point returns ICT_ERR_NO_DEVICE.
+ *
+ * Each entry point names the reference interface it replaces (file:line under the
+ * reference checkout).  Names of quantities follow the reference: points (pt3d), patches,
+ * steepest-descent (sd) images, Hessian, pose coefficients p = [tx ty tz wx wy wz].
+ */
+#ifndef ICTRACK_H
+#define ICTRACK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICT_VERSION 100          /* 0.1.0 */
+#define ICT_MAX_LEVELS 8         /* lv_f <= 7 */
+
+enum {
+  ICT_OK = 0,
+  ICT_ERR_NO_DEVICE = 1,         /* no CUDA device / driver: the library never falls back to a CPU path */
+  ICT_ERR_BAD_ARG = 2,
+  ICT_ERR_CUDA = 3,
+  ICT_ERR_NOMEM = 4,
+  ICT_ERR_UNSUPPORTED = 5
+};
+
+/* Bit-compatible with CTR::optparam, utilities.h:46-61 (same field order, bool = 1 byte). */
+typedef struct ict_optparam {
+  int maxpttrack;                /* max points per track, multiple of 4 (run_io_reprojection_test.cpp:122-126) */
+  int psz;                       /* patch size */
+  int pszd2;                     /* psz/2 */
+  int pszd2m3;                   /* psz + psz/2 - 1 */
+  int novals;                    /* psz*psz */
+  int lv_f;                      /* coarsest pyramid level (first processed) */
+  int lv_l;                      /* finest pyramid level (last processed) */
+  unsigned char donorm;          /* point-cloud / pose normalisation */
+  unsigned char dopatchnorm;     /* patch mean subtraction */
+  int maxiter;
+  float normdp_ratio;
+  int verbosity;
+} ict_optparam;
+
+/* Fills the derived fields the way both reference drivers do
+ * (run_io_reprojection_test.cpp:112-127, run_track_nposes.cpp:47-54). */
+void ict_optparam_init(ict_optparam* op, int lv_f, int lv_l, int psz, int maxiter, float normdp_ratio,
+                       int donorm, int dopatchnorm, int maxpttrack, int verbosity);
+
+int ict_version(void);
+const char* ict_last_error(void);
+int ict_device_count(void);                      /* 0 when no usable CUDA device */
+int ict_set_device(int dev);
+
+/* ---- a2: per-level intrinsics, CamClass::CamClass camera.cpp:14-45 -------------------------------
+ * out[8*l + {0..7}] = fx fy cx cy swo sho sw sh of level l (same arithmetic: float(1/pow(2,l)) * orig). */
+int ict_camera_levels(int noscales, const float fc[2], const float cc[2], const int wh[2], int padding,
+                      float* out);
+
+/* ---- a3: util_constructpyramide, utilities.cpp:14-52 ---------------------------------------------
+ * Layout of one pyramid plane set: level l is a row-major (h/2^l + 2*pad) x (w/2^l + 2*pad) float plane at
+ * float offset level_off[l]; returns the total number of floats of one plane set (or -1 on bad input).
+ * w and h must be divisible by 2^lv_f (camera.h:12-13 states the same assumption). */
+int64_t ict_pyramid_layout(int w, int h, int lv_f, int pad, int64_t* level_off, int* sw, int* sh);
+
+/* Host image in, host planes out; the work is done on the GPU (upload, build, download). */
+int ict_pyramid_build(const float* img, int w, int h, int lv_f, int pad,
+                      float* out_I, float* out_dx, float* out_dy);
+
+/* ---- device-resident frame store ------------------------------------------------------------------
+ * Holds the I/dx/dy pyramids of nframes frames in HBM.  Replaces the per-frame cv::Mat arrays the drivers keep
+ * (run_io_reprojection_test.cpp:143-158, run_track_nposes.cpp:157-181). */
+typedef struct ict_frames ict_frames;
+ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad);
+void ict_frames_destroy(ict_frames* fs);
+/* count frames, each h*w, contiguous, from HOST memory: H2D copy + on-device pyramid build. */
+int ict_frames_upload(ict_frames* fs, int first, int count, const float* imgs);
+int ict_frames_upload_u8(ict_frames* fs, int first, int count, const unsigned char* imgs);   /* cv::imread(GRAYSCALE) payload */
+/* Same, the images already being in device memory (float or u8); stream is a cudaStream_t (NULL = default). */
+int ict_frames_build_dev(ict_frames* fs, int first, int count, const float* imgs_dev, void* stream);
+int ict_frames_build_dev_u8(ict_frames* fs, int first, int count, const unsigned char* imgs_dev, void* stream);
+/* Download one frame's padded planes (any of the outputs may be NULL). */
+int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy);
+
+/* ---- tracker: OdometerClass + PoseClass + CamClass for a BATCH of independent tracks -------------------
+ * One track == one Set3Dpoints -> SetPose -> TrackPose of the reference (odometer.cpp:171-426).
+ * op is copied at creation; padding of the camera == op->psz as in both drivers
+ * (run_io_reprojection_test.cpp:189, run_track_nposes.cpp:185). */
+typedef struct ict_tracker ict_tracker;
+ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2]);
+void ict_tracker_destroy(ict_tracker* tr);
+/* later changes of the caller's optparam (run_track_nposes.cpp:281 flips dopatchnorm mid-run) */
+int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
+
+/* Per-iteration trace record, ICT_TRACE_FLOATS floats:
+ *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame
+ * Track t owns records [t*trace_cap, (t+1)*trace_cap); unused records have level = -1. */
+#define ICT_TRACE_FLOATS 16
+
+/* Set3Dpoints for T tracks (odometer.cpp:171-239).  Track t has points pt_off[t]..pt_off[t+1]-1; its points are
+ * stored as the reference expects them: X block, Y block, Z block, each of length n_t, at pts + 3*pt_off[t].
+ * HOST pointers.  With donorm the reference centres the CALLER's array in place (odometer.cpp:207-212); pass
+ * mutate_caller=1 to get the same side effect (pts is then written). */
+int ict_tracker_set_points(ict_tracker* tr, int T, const int64_t* pt_off, double* pts, int mutate_caller);
+/* Same with device pointers (pt_off_dev: int64[T+1], pts_dev: double[3*total]); nothing is written back.
+ * max_pts = the largest n_t (the host needs it to size the launch). */
+int ict_tracker_set_points_dev(ict_tracker* tr, int T, const int64_t* pt_off_dev, const double* pts_dev,
+                               int64_t total_pts, int max_pts, void* stream);
+
+/* SetPose + TrackPose for the T tracks set above (odometer.cpp:241-426), host buffers:
+ *   ref_frame[t], new_frame[t]  indices into fs          p_in, p_out  double[T*6]
+ *   iters  int[T*(lv_f-lv_l+1)] iterations run per level, coarse to fine (may be NULL)
+ *   trace  float[T*trace_cap*ICT_TRACE_FLOATS] or NULL
+ *   npixres int64[T] pixel-residuals evaluated per track (may be NULL). */
+int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame, const int* new_frame,
+                    const double* p_in, double* p_out, int* iters, float* trace, int trace_cap,
+                    int64_t* npixres);
+/* Device-pointer form; nothing crosses PCIe.  All pointers are device memory; trace_dev/iters_dev/npixres_dev
+ * may be NULL. */
+int ict_track_batch_dev(ict_tracker* tr, const ict_frames* fs, const int* ref_frame_dev, const int* new_frame_dev,
+                        const double* p_in_dev, double* p_out_dev, int* iters_dev, float* trace_dev,
+                        int trace_cap, int64_t* npixres_dev, void* stream);
+
+/* One forward (step=+1) or backward (step=-1) chain of run_track_nposes.cpp:232-239 / :251-258 for all T tracks:
+ * for k in 0..nsteps-1: SetPose(p, frame[first+k*step] as ref, frame[first+(k+1)*step] as new); TrackPose(p).
+ * poses_out: double[(nsteps+1)*T*6], entry 0 = p_in. Host buffers. */
+int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nsteps, int step,
+                       const double* p_in, double* poses_out, int* iters, int64_t* npixres);
+
+/* Reference 2-D points of the LAST SetPose at level lv_l (OdometerClass::Get2DPoints, odometer.h:30):
+ * out float[2*n_t] per track at 2*pt_off[t]: x block then y block. Host buffer. */
+int ict_tracker_get_2dpoints(ict_tracker* tr, float* out);
+
+/* ---- single-pair convenience == the body of run_io_reprojection_test.cpp:157-224 -------------------
+ * imgA/imgB: host h*w floats (uint8-valued as produced by imread+convertTo).  pt3d: X block, Y block, Z block
+ * (npts each; written if op->donorm, like the reference).  iters/trace may be NULL. */
+int ict_track_pair(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2],
+                   const float* imgA, const float* imgB, double* pt3d, int npts,
+                   const double p_in[6], double p_out[6], int* iters, float* trace, int trace_cap);
+
+/* ---- f1 (next row): NCC hypothesis scoring, run_track_nposes.cpp:271-355 ------------------------------
+ * For every point of every track: mean-subtracted psz x psz patches at pt2d_back/refe/forw in frames
+ * frame_b/frame_r/frame_f at level lv_l, normalised, corr = weighted max(0, dot).  pt2d_*: float[2*total] laid out
+ * like ict_tracker_get_2dpoints.  out_corr: float[total]. */
+int ict_ncc_score(ict_tracker* tr, const ict_frames* fs, int frame_b, int frame_r, int frame_f,
+                  int nback, int nfwd, const float* pt2d_back, const float* pt2d_refe, const float* pt2d_forw,
+                  float* out_corr);
+
+/* Kernel launches issued by this library since the last reset (for bench.py's gpu_launches). */
+int64_t ict_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICTRACK_H */
