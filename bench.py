@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the inverse-compositional GN tracking path on B200 (one process per GPU).
+
+Workload (BASELINE.json configs[4] per-GPU share == configs[2] geometry): S independent synthetic 1080p frame
+pairs per GPU ("sequences" advancing one frame), T = 4096 independent tracks each, every track 4 points with
+32x32 patches, 4-level pyramid, maxiter 10, normdp_ratio 0.01.  configs[1] (one 100-point template over 100
+frames) cannot occupy a GPU and is a parity-test case (tests/test_gpu_parity.py::test_sequence_chain).
+
+One step = for every local sequence: build the I/dx/dy pyramids of both frames on the device
+(util_constructpyramide), then Set3Dpoints -> SetPose -> TrackPose for all S*T tracks (all levels, all GN
+iterations, convergence test on device).
+  value  : pixel-residuals/s with the uint8 frames, points and poses already resident in HBM
+  e2e    : the same through the host-buffer C ABI (pinned host memory -> H2D -> kernels -> D2H) every step
+  roofline: k_track, algorithmic 32 B per pixel-residual over its CUDA-event time
+Weak scaling: per-GPU work is fixed; ranks share nothing on the hot path, poses are all-gathered (NCCL) once
+after the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PIXRES = 32.0   # 4 B pat_ref + 6*4 B steepest-descent values + 4 B new-frame texel
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self.stop_ev = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(rank, S, T, P, psz, w, h, lv_f, ntex):
+    """S frame pairs (uint8) + S*T tracks of P plane points each; deterministic in (rank, s)."""
+    from invcompcamtrack_b200 import synth
+    scenes = {}
+    frames = np.empty((2 * S, h, w), np.uint8)
+    pts = np.empty(3 * S * T * P, np.float64)
+    p_gt = np.zeros((S, 6))
+    fc = cc = wh = None
+    for s in range(S):
+        gs = rank * S + s
+        tex_id = gs % ntex
+        if tex_id not in scenes:
+            scenes[tex_id] = synth.Scene(tex_id, w, h)
+        sc = scenes[tex_id]
+        fc, cc, wh = sc.fc, sc.cc, sc.wh
+        p_gt[s] = sc.random_motion(gs)
+        frames[2 * s] = sc.render(np.zeros(6))
+        frames[2 * s + 1] = sc.render(p_gt[s])
+        # T tracks x P points: one draw of T*P points, regrouped per track as X block, Y block, Z block
+        q = sc.points(gs, T * P, psz, lv_f).reshape(3, T, P)
+        pts[3 * s * T * P:3 * (s + 1) * T * P] = np.ascontiguousarray(q.transpose(1, 0, 2)).reshape(-1)
+    pt_off = np.arange(S * T + 1, dtype=np.int64) * P
+    ref = np.repeat(np.arange(S, dtype=np.int32) * 2, T)
+    new = ref + 1
+    return dict(frames=frames, pts=pts, pt_off=pt_off, ref=ref, new=new, p_gt=p_gt, fc=fc, cc=cc, wh=wh)
+
+
+def cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, threads, use_ref):
+    """Times the CPU implementation (oracle port or oracle/_ref) on `seqs` sequences of the same workload."""
+    from oracle import oracle as O
+    orc = O.OracleLib()
+    op = O.make_optparam(**op_kw)
+    seqs = min(seqs, S)
+    t0 = time.perf_counter()
+    pyr = [orc.pyramid_build(wl["frames"][f].astype(np.float32), lv_f, psz) for f in range(2 * seqs)]
+    t_pyr = time.perf_counter() - t0
+    n = seqs * T
+    args = (op, wl["fc"], wl["cc"], wl["wh"], [q[0] for q in pyr], [q[1] for q in pyr], [q[2] for q in pyr],
+            wl["pt_off"][:n + 1], wl["pts"][:3 * n * P].copy(), wl["ref"][:n], wl["new"][:n], np.zeros((n, 6)))
+    # pixel-residual count always from the instrumented port (the reference classes do not expose it)
+    counted = orc.track_batch(*args, nthreads=threads)
+    npix = int(counted["npixres"].sum())
+    if use_ref and O.RefLib.available():
+        ref = O.RefLib()
+        t0 = time.perf_counter()
+        ref.track_batch(*args, nthreads=threads)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+    else:
+        t0 = time.perf_counter()
+        orc.track_batch(*args, nthreads=threads)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    return dict(value=npix / dt, tracks_per_s=n / dt, seconds=dt, kind=kind, npix=npix, tracks=n,
+                pyramid_ms_per_frame=1e3 * t_pyr / (2 * seqs), p_out=counted["p_out"], iters=counted["iters"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqs", type=int, default=env_int("ICT_BENCH_SEQS", 32), help="sequences (frame pairs) per GPU")
+    ap.add_argument("--tracks", type=int, default=4096, help="tracks per sequence")
+    ap.add_argument("--points", type=int, default=4, help="points per track")
+    ap.add_argument("--psz", type=int, default=32)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--cpu-seqs", type=int, default=env_int("ICT_BENCH_CPU_SEQS", 2), help="sequences in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--textures", type=int, default=4, help="distinct textures shared by the sequences (setup time)")
+    a = ap.parse_args()
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    S, T, P, psz, w, h, lv_f = a.seqs, a.tracks, a.points, a.psz, a.width, a.height, 3
+    op_kw = dict(lv_f=lv_f, lv_l=0, psz=psz, maxiter=10, normdp_ratio=0.01, donorm=0, dopatchnorm=0, maxpttrack=P)
+    config = {"workload": "S=%d synthetic %dx%d frame pairs x %d tracks x %d points x %dx%d patches per GPU, "
+                          "4-level pyramid, maxiter 10, normdp_ratio 0.01 (BASELINE configs[4] per-GPU share)"
+                          % (S, w, h, T, P, psz, psz),
+              "seqs_per_gpu": S, "tracks_per_seq": T, "points_per_track": P, "psz": psz, "frame": [w, h],
+              "levels": lv_f + 1, "l2_policy": "inputs larger than L2: %.0f MB of pyramids + %.0f MB of uint8 frames per step"
+              % (S * 2 * 3 * 12.52, S * 2 * w * h / 1e6)}
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+    # ------------------------------------------------------------------------------------------------
+    if a.impl == "reference":
+        # the reference's own CPU implementation on the host cores: rank 0 only, bounded sample per step
+        if rank != 0:
+            return 0
+        from oracle import oracle as O
+        use_ref = O.RefLib.available()
+        seqs = max(1, min(a.cpu_seqs, S))
+        wl = make_workload(0, seqs, T, P, psz, w, h, lv_f, a.textures)
+        times, res = [], None
+        for k in range(a.warmup + a.steps):
+            res = cpu_sample(wl, op_kw, seqs, T, P, psz, w, h, lv_f, seqs, cores, use_ref)
+            if k >= a.warmup:
+                times.append(res["seconds"])
+        dt = float(np.mean(times))
+        val = res["npix"] / dt
+        sample = ("%d sequences x %d tracks per step (of %d per GPU); %s; span Set3Dpoints->SetPose->TrackPose, "
+                  "pyramids built beforehand (%.1f ms/frame, 1 thread)"
+                  % (seqs, T, S, "reference sources (utilities/camera/pose/odometer.cpp) compiled against the stand-in "
+                     "Eigen/OpenCV headers of oracle/shim" if res["kind"] == "reference" else "oracle port (plain C)",
+                     res["pyramid_ms_per_frame"]))
+        line = {"impl": "reference", "metric": "GN pixel-residuals/s", "value": val, "unit": "pixel-residuals/s",
+                "tracks_per_s": res["tracks"] / dt, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "pixel-residuals/s", "cores": cores, "kind": res["kind"],
+                                 "sample": sample},
+                "e2e": {"value": val, "unit": "pixel-residuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import invcompcamtrack_b200 as ict
+
+    if not torch.cuda.is_available() or ict.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the tracking path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    ict.lib().ict_set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = make_workload(rank, S, T, P, psz, w, h, lv_f, a.textures)
+    NT = S * T
+    L = lv_f + 1
+    op = ict.make_optparam(**op_kw)
+    frames = ict.Frames(2 * S, w, h, lv_f, psz)
+    tracker = ict.Tracker(op, wl["fc"], wl["cc"], wl["wh"])
+
+    # device-resident inputs
+    d_frames = torch.from_numpy(wl["frames"]).to(dev)
+    d_pts = torch.from_numpy(wl["pts"]).to(dev)
+    d_off = torch.from_numpy(wl["pt_off"]).to(dev)
+    d_ref = torch.from_numpy(wl["ref"]).to(dev)
+    d_new = torch.from_numpy(wl["new"]).to(dev)
+    d_pin = torch.zeros(NT, 6, dtype=torch.float64, device=dev)
+    d_pout = torch.zeros(NT, 6, dtype=torch.float64, device=dev)
+    d_iters = torch.zeros(NT, L, dtype=torch.int32, device=dev)
+    d_npix = torch.zeros(NT, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+
+    def step_dev(k=None):
+        frames.build_dev(0, 2 * S, d_frames.data_ptr(), u8=True, stream=stream)
+        tracker.set_points_dev(NT, d_off.data_ptr(), d_pts.data_ptr(), NT * P, P, stream=stream)
+        if k is not None:
+            ev_k0[k].record()
+        tracker.track_batch_dev(frames, d_ref.data_ptr(), d_new.data_ptr(), d_pin.data_ptr(), d_pout.data_ptr(),
+                                iters_ptr=d_iters.data_ptr(), npix_ptr=d_npix.data_ptr(), stream=stream)
+        if k is not None:
+            ev_k1[k].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_dev()
+    barrier()
+    ict.launch_count(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.steps):
+        step_dev(k)
+    e1.record()
+    barrier()
+    launches = ict.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    ms_kernel = float(np.mean([ev_k0[k].elapsed_time(ev_k1[k]) for k in range(a.steps)]))
+    npix_step = int(d_npix.sum().item())
+    iters_mean = float(d_iters.sum(dim=1).double().mean().item())
+
+    # ---- e2e: host buffers through the C ABI, H2D/D2H inside the timed region ----------------------------
+    e2e = None
+    if not a.no_e2e:
+        h_frames = torch.from_numpy(wl["frames"]).pin_memory()
+        h_pts = torch.from_numpy(wl["pts"]).pin_memory()
+        h_pin = torch.zeros(NT, 6, dtype=torch.float64).pin_memory()
+        h_pout = torch.zeros(NT, 6, dtype=torch.float64).pin_memory()
+        h_iters = torch.zeros(NT, L, dtype=torch.int32).pin_memory()
+        h_npix = torch.zeros(NT, dtype=torch.int64).pin_memory()
+        import ctypes as C
+        lib = ict.lib()
+        v = C.c_void_p
+
+        def step_host():
+            frames.upload_ptr(0, 2 * S, h_frames.data_ptr(), u8=True)
+            rc = lib.ict_tracker_set_points(tracker.h_, NT, v(wl["pt_off"].ctypes.data), v(h_pts.data_ptr()), 0)
+            rc |= lib.ict_track_batch(tracker.h_, frames.h_, v(wl["ref"].ctypes.data), v(wl["new"].ctypes.data),
+                                      v(h_pin.data_ptr()), v(h_pout.data_ptr()), v(h_iters.data_ptr()), None, 0,
+                                      v(h_npix.data_ptr()))
+            if rc:
+                raise ict.IctError(lib.ict_last_error().decode())
+
+        for _ in range(min(a.warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(a.steps):
+            step_host()
+        f1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_e2e = max(f0.elapsed_time(f1), 0.0)
+        if not torch.equal(h_pout.to(dev), d_pout):
+            raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
+        h2d = h_frames.numel() + 8 * h_pts.numel() + 8 * wl["pt_off"].size + 4 * 2 * NT + 48 * NT
+        d2h = 48 * NT + 4 * L * NT + 8 * NT
+        e2e = dict(ms=ms_e2e, wall_ms=1e3 * wall, h2d=int(h2d), d2h=int(d2h), npix=int(h_npix.sum().item()))
+    clocks = None
+    sampler.stop_ev.set()
+    sampler.join(timeout=3)
+    clocks = sampler.summary()
+
+    # ---- max over ranks, whole-job aggregate ------------------------------------------------------------
+    stats = torch.tensor([ms_total, ms_kernel, e2e["ms"] if e2e else 0.0, float(npix_step)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        # the one collective of the path: gather the per-track poses (6 f64) and iteration counts
+        gathered = [torch.empty_like(d_pout) for _ in range(world)]
+        dist.all_gather(gathered, d_pout)
+        ms_total, ms_kernel, ms_e2e_all = mx[0].item(), mx[1].item(), mx[2].item()
+        npix_job = sm[3].item()
+    else:
+        ms_e2e_all = e2e["ms"] if e2e else 0.0
+        npix_job = float(npix_step)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        value = npix_job * a.steps / (ms_total * 1e-3)
+        tracks_s = NT * world * a.steps / (ms_total * 1e-3)
+        achieved = npix_step * BYTES_PER_PIXRES / (ms_kernel * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_track_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": "GN pixel-residuals/s", "value": value, "unit": "pixel-residuals/s",
+                "tracks_per_s": tracks_s, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "pixel_residuals_per_step_per_gpu": npix_step, "gn_iterations_per_track": iters_mean,
+                "roofline": {"bound": "hbm", "kernel": "k_track<32,false>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_pixel_residual": BYTES_PER_PIXRES,
+                             "kernel_ms_per_launch": ms_kernel,
+                             "kernel_share_of_step": ms_kernel / (ms_total / a.steps)},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if e2e:
+            line["e2e"] = {"value": npix_job * a.steps / (ms_e2e_all * 1e-3), "unit": "pixel-residuals/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "ms_per_step": ms_e2e_all / a.steps, "wall_ms_per_step": e2e["wall_ms"] / a.steps,
+                           "tracks_per_s": NT * world * a.steps / (ms_e2e_all * 1e-3)}
+        if world == 1 and not a.no_cpu:
+            seqs = max(1, min(a.cpu_seqs, S))
+            cb = cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, cores, use_ref=False)
+            # parity spot-check of the benchmark's own result against the oracle on the sampled tracks
+            g = d_pout[:cb["tracks"]].cpu().numpy()
+            same = float((d_iters[:cb["tracks"]].cpu().numpy() == cb["iters"]).mean())
+            line["cpu_baseline"] = {
+                "value": cb["value"], "unit": "pixel-residuals/s", "cores": cores, "kind": cb["kind"],
+                "tracks_per_s": cb["tracks_per_s"],
+                "sample": "%d of the %d sequences (%d tracks), %.1f s, oracle port (plain C, -O3 -msse4 -mavx), OpenMP "
+                          "over tracks; span Set3Dpoints->SetPose->TrackPose; pyramids %.1f ms/frame on 1 thread extra"
+                          % (seqs, S, cb["tracks"], cb["seconds"], cb["pyramid_ms_per_frame"]),
+                "parity_vs_gpu": {"max_abs_pose_diff": float(np.abs(g - cb["p_out"]).max()),
+                                  "frac_identical_iteration_counts": same}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

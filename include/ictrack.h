@@ -102,8 +102,10 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
 
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:
  *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame
+ *   [16..21] sum_k |sd_k * pdiff| — filled by the CPU oracle only (the scale fp32 summation noise is relative to;
+ *            used to normalise the J^T r parity gate), 0 from the GPU   [22..23] reserved
  * Track t owns records [t*trace_cap, (t+1)*trace_cap); unused records have level = -1. */
-#define ICT_TRACE_FLOATS 16
+#define ICT_TRACE_FLOATS 24
 
 /* Set3Dpoints for T tracks (odometer.cpp:171-239).  Track t has points pt_off[t]..pt_off[t+1]-1; its points are
  * stored as the reference expects them: X block, Y block, Z block, each of length n_t, at pts + 3*pt_off[t].

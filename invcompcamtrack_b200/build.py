@@ -1,0 +1,62 @@
+"""In-tree build of libictrack.so (nvcc, sm_100a only) and of the host-side C++ drivers.
+
+    python -m invcompcamtrack_b200.build          # library + drivers
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libictrack.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -fmad=false: the reference is built without FMA (CMakeLists.txt:4), contraction would change its fp32 results
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-ccbin", "g++"]
+LIB_SOURCES = ["ict_kernels.cu", "ict_kernels_big.cu", "ict_capi.cu"]
+LIB_DEPS = LIB_SOURCES + ["ict_kernels.cuh", "ict_device.cuh", os.path.join("..", "..", "include", "ictrack.h")]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force=False, verbose=False):
+    deps = [os.path.join(CSRC, d) for d in LIB_DEPS]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in LIB_SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_drivers(force=False):
+    """run_track / run_track_nposes: host C++ (reference class interface) linked against libictrack.so."""
+    host = os.path.join(CSRC, "host")
+    out = []
+    for name in ("run_track", "run_track_nposes"):
+        src = os.path.join(host, name + ".cpp")
+        if not os.path.exists(src):
+            continue
+        exe = os.path.join(HERE, "bin", name)
+        deps = [src] + [os.path.join(host, f) for f in os.listdir(host)] + [LIB]
+        if force or _stale(exe, deps):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            srcs = [src] + [os.path.join(host, f) for f in ("camera.cpp", "pose.cpp", "odometer.cpp", "utilities.cpp")]
+            subprocess.run(["g++", "-O2", "-std=c++14", "-I", host, "-I", os.path.join(HERE, "..", "include"), "-o", exe]
+                           + srcs + ["-L", HERE, "-lictrack", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."], check=True)
+        out.append(exe)
+    return out
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    print(build_library(force=force, verbose="-v" in sys.argv))
+    for e in build_drivers(force=force):
+        print(e)

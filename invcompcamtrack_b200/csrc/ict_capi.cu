@@ -1,0 +1,546 @@
+// ict_capi.cu — the C ABI of libictrack.so (include/ictrack.h): host-side orchestration only.
+// Every compute entry point runs CUDA kernels from ict_kernels.cu; there is no CPU fallback.
+#include "ict_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace ict;
+
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return fail(ICT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+  } while (0)
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(ICT_ERR_NO_DEVICE, "no CUDA device: libictrack has no CPU fallback");
+  }
+  return ICT_OK;
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+void ict_optparam_init(ict_optparam* op, int lv_f, int lv_l, int psz, int maxiter, float normdp_ratio, int donorm,
+                       int dopatchnorm, int maxpttrack, int verbosity) {
+  memset(op, 0, sizeof(*op));
+  op->lv_f = lv_f;
+  op->lv_l = lv_l;
+  op->psz = psz;
+  op->pszd2 = psz / 2;                 // run_io_reprojection_test.cpp:115
+  op->pszd2m3 = psz + op->pszd2 - 1;   // :116
+  op->novals = psz * psz;              // :117
+  op->maxiter = maxiter;
+  op->normdp_ratio = normdp_ratio;
+  op->donorm = donorm ? 1 : 0;
+  op->dopatchnorm = dopatchnorm ? 1 : 0;
+  const int r = maxpttrack % 4;        // SSEMULTIPL padding, :123-126
+  op->maxpttrack = r > 0 ? maxpttrack + (4 - r) : maxpttrack;
+  op->verbosity = verbosity;
+}
+
+int ict_version(void) { return ICT_VERSION; }
+const char* ict_last_error(void) { return g_err.c_str(); }
+
+int ict_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int ict_set_device(int dev) {
+  if (require_device()) return ICT_ERR_NO_DEVICE;
+  CU(cudaSetDevice(dev));
+  return ICT_OK;
+}
+
+int64_t ict_launch_count(int reset) { return launch_count(reset); }
+
+// ---- camera (camera.cpp:32-43) ------------------------------------------------------------------------
+int ict_camera_levels(int noscales, const float fc[2], const float cc[2], const int wh[2], int padding,
+                      float* out) {
+  if (noscales < 1 || noscales > ICT_MAX_LEVELS) return fail(ICT_ERR_BAD_ARG, "noscales out of range");
+  for (int i = 0; i < noscales; ++i) {
+    const float sc_fct = (float)(1 / pow(2, i));
+    float* o = out + 8 * i;
+    o[0] = sc_fct * fc[0];
+    o[1] = sc_fct * fc[1];
+    o[2] = sc_fct * cc[0];
+    o[3] = sc_fct * cc[1];
+    o[4] = sc_fct * (float)wh[0];
+    o[5] = sc_fct * (float)wh[1];
+    o[6] = o[4] + 2 * padding;
+    o[7] = o[5] + 2 * padding;
+  }
+  return ICT_OK;
+}
+
+static void fill_cam(CamLevels& cam, int noscales, const float fc[2], const float cc[2], const int wh[2],
+                     int padding) {
+  float lv[8 * ICT_MAX_LEVELS];
+  ict_camera_levels(noscales, fc, cc, wh, padding, lv);
+  memset(&cam, 0, sizeof(cam));
+  for (int l = 0; l < noscales; ++l) {
+    cam.fx[l] = lv[8 * l + 0];
+    cam.fy[l] = lv[8 * l + 1];
+    cam.cx[l] = lv[8 * l + 2];
+    cam.cy[l] = lv[8 * l + 3];
+    cam.swo[l] = lv[8 * l + 4];
+    cam.sho[l] = lv[8 * l + 5];
+    cam.width[l] = (int)lv[8 * l + 6];   // float getsw() received as `const int width`, odometer.cpp:286
+  }
+}
+
+// ---- pyramid ------------------------------------------------------------------------------------------
+int64_t ict_pyramid_layout(int w, int h, int lv_f, int pad, int64_t* level_off, int* sw, int* sh) {
+  if (w <= 0 || h <= 0 || lv_f < 0 || lv_f >= ICT_MAX_LEVELS || pad < 0) return -1;
+  if ((w % (1 << lv_f)) || (h % (1 << lv_f))) return -1;   // camera.h:12-13: sizes divisible by 2 per level
+  int64_t tot = 0;
+  for (int l = 0; l <= lv_f; ++l) {
+    const int a = (w >> l) + 2 * pad, b = (h >> l) + 2 * pad;
+    if (level_off) level_off[l] = tot;
+    if (sw) sw[l] = a;
+    if (sh) sh[l] = b;
+    tot += (int64_t)a * b;
+  }
+  return tot;
+}
+
+struct ict_frames {
+  int nframes, w, h, lv_f, pad;
+  int64_t plane_floats;
+  int64_t level_off[ICT_MAX_LEVELS];
+  int sw[ICT_MAX_LEVELS], sh[ICT_MAX_LEVELS];
+  float *I, *dx, *dy;
+  FrameDesc* desc;
+  DevBuf stage;
+};
+
+ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
+  if (require_device()) return nullptr;
+  ict_frames* fs = new ict_frames();
+  fs->nframes = nframes; fs->w = w; fs->h = h; fs->lv_f = lv_f; fs->pad = pad;
+  fs->I = fs->dx = fs->dy = nullptr;
+  fs->desc = nullptr;
+  fs->plane_floats = ict_pyramid_layout(w, h, lv_f, pad, fs->level_off, fs->sw, fs->sh);
+  if (fs->plane_floats < 0 || nframes <= 0) {
+    fail(ICT_ERR_BAD_ARG, "ict_frames_create: w,h must be divisible by 2^lv_f, nframes > 0");
+    delete fs;
+    return nullptr;
+  }
+  const size_t bytes = sizeof(float) * (size_t)fs->plane_floats * nframes;
+  if (cudaMalloc(&fs->I, bytes) != cudaSuccess || cudaMalloc(&fs->dx, bytes) != cudaSuccess ||
+      cudaMalloc(&fs->dy, bytes) != cudaSuccess || cudaMalloc(&fs->desc, sizeof(FrameDesc) * nframes) != cudaSuccess) {
+    fail(ICT_ERR_NOMEM, "ict_frames_create: cudaMalloc failed");
+    cudaGetLastError();
+    ict_frames_destroy(fs);
+    return nullptr;
+  }
+  std::vector<FrameDesc> d(nframes);
+  for (int f = 0; f < nframes; ++f) {
+    memset(&d[f], 0, sizeof(FrameDesc));
+    for (int l = 0; l <= lv_f; ++l) {
+      d[f].I[l] = fs->I + (size_t)f * fs->plane_floats + fs->level_off[l];
+      d[f].dx[l] = fs->dx + (size_t)f * fs->plane_floats + fs->level_off[l];
+      d[f].dy[l] = fs->dy + (size_t)f * fs->plane_floats + fs->level_off[l];
+    }
+  }
+  if (cudaMemcpy(fs->desc, d.data(), sizeof(FrameDesc) * nframes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    fail(ICT_ERR_CUDA, "ict_frames_create: descriptor upload failed");
+    ict_frames_destroy(fs);
+    return nullptr;
+  }
+  return fs;
+}
+
+void ict_frames_destroy(ict_frames* fs) {
+  if (!fs) return;
+  if (fs->I) cudaFree(fs->I);
+  if (fs->dx) cudaFree(fs->dx);
+  if (fs->dy) cudaFree(fs->dy);
+  if (fs->desc) cudaFree(fs->desc);
+  fs->stage.release();
+  delete fs;
+}
+
+static int frames_range_ok(const ict_frames* fs, int first, int count) {
+  if (!fs) return fail(ICT_ERR_BAD_ARG, "null frame store");
+  if (first < 0 || count < 0 || first + count > fs->nframes) return fail(ICT_ERR_BAD_ARG, "frame range out of bounds");
+  return ICT_OK;
+}
+
+static int frames_build(ict_frames* fs, int first, int count, const float* f32, const unsigned char* u8,
+                        cudaStream_t st) {
+  CU(launch_pyramid(f32, u8, count, fs->w, fs->h, fs->lv_f, fs->pad, fs->I + (size_t)first * fs->plane_floats,
+                    fs->dx + (size_t)first * fs->plane_floats, fs->dy + (size_t)first * fs->plane_floats,
+                    fs->plane_floats, fs->level_off, st));
+  return ICT_OK;
+}
+
+int ict_frames_build_dev(ict_frames* fs, int first, int count, const float* imgs_dev, void* stream) {
+  if (frames_range_ok(fs, first, count)) return ICT_ERR_BAD_ARG;
+  return frames_build(fs, first, count, imgs_dev, nullptr, (cudaStream_t)stream);
+}
+int ict_frames_build_dev_u8(ict_frames* fs, int first, int count, const unsigned char* imgs_dev, void* stream) {
+  if (frames_range_ok(fs, first, count)) return ICT_ERR_BAD_ARG;
+  return frames_build(fs, first, count, nullptr, imgs_dev, (cudaStream_t)stream);
+}
+
+int ict_frames_upload(ict_frames* fs, int first, int count, const float* imgs) {
+  if (frames_range_ok(fs, first, count)) return ICT_ERR_BAD_ARG;
+  const size_t bytes = sizeof(float) * (size_t)fs->w * fs->h * count;
+  CU(fs->stage.reserve(bytes));
+  CU(cudaMemcpyAsync(fs->stage.p, imgs, bytes, cudaMemcpyHostToDevice, 0));
+  return frames_build(fs, first, count, fs->stage.as<float>(), nullptr, 0);
+}
+int ict_frames_upload_u8(ict_frames* fs, int first, int count, const unsigned char* imgs) {
+  if (frames_range_ok(fs, first, count)) return ICT_ERR_BAD_ARG;
+  const size_t bytes = (size_t)fs->w * fs->h * count;
+  CU(fs->stage.reserve(bytes));
+  CU(cudaMemcpyAsync(fs->stage.p, imgs, bytes, cudaMemcpyHostToDevice, 0));
+  return frames_build(fs, first, count, nullptr, fs->stage.as<unsigned char>(), 0);
+}
+
+int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy) {
+  if (frames_range_ok(fs, frame, 1)) return ICT_ERR_BAD_ARG;
+  const size_t bytes = sizeof(float) * (size_t)fs->plane_floats, o = (size_t)frame * fs->plane_floats;
+  if (out_I) CU(cudaMemcpy(out_I, fs->I + o, bytes, cudaMemcpyDeviceToHost));
+  if (out_dx) CU(cudaMemcpy(out_dx, fs->dx + o, bytes, cudaMemcpyDeviceToHost));
+  if (out_dy) CU(cudaMemcpy(out_dy, fs->dy + o, bytes, cudaMemcpyDeviceToHost));
+  return ICT_OK;
+}
+
+int ict_pyramid_build(const float* img, int w, int h, int lv_f, int pad, float* out_I, float* out_dx,
+                      float* out_dy) {
+  if (require_device()) return ICT_ERR_NO_DEVICE;
+  ict_frames* fs = ict_frames_create(1, w, h, lv_f, pad);
+  if (!fs) return ICT_ERR_BAD_ARG;
+  int rc = ict_frames_upload(fs, 0, 1, img);
+  if (rc == ICT_OK) rc = ict_frames_download(fs, 0, out_I, out_dx, out_dy);
+  ict_frames_destroy(fs);
+  return rc;
+}
+
+// ---- tracker ------------------------------------------------------------------------------------------
+struct ict_tracker {
+  ict_optparam op;
+  CamLevels cam;
+  float fc[2], cc[2];
+  int wh[2];
+  int T = 0;
+  int64_t total = 0;
+  int max_pts = 0;
+  std::vector<int64_t> h_off;
+  bool have_2d = false;
+  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
+};
+
+ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2]) {
+  if (require_device()) return nullptr;
+  if (!op || op->psz < 1 || op->lv_f < op->lv_l || op->lv_l < 0 || op->lv_f >= ICT_MAX_LEVELS || op->maxpttrack < 1) {
+    fail(ICT_ERR_BAD_ARG, "ict_tracker_create: bad optparam");
+    return nullptr;
+  }
+  ict_tracker* tr = new ict_tracker();
+  tr->op = *op;
+  memcpy(tr->fc, fc, sizeof(tr->fc));
+  memcpy(tr->cc, cc, sizeof(tr->cc));
+  memcpy(tr->wh, wh, sizeof(tr->wh));
+  fill_cam(tr->cam, op->lv_f + 1, fc, cc, wh, op->psz);   // padding = psz, run_io_reprojection_test.cpp:189
+  return tr;
+}
+
+void ict_tracker_destroy(ict_tracker* tr) {
+  if (!tr) return;
+  DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
+                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big};
+  for (DevBuf* x : b) x->release();
+  delete tr;
+}
+
+int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op) {
+  if (!tr || !op) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (op->psz != tr->op.psz || op->lv_f != tr->op.lv_f)
+    return fail(ICT_ERR_BAD_ARG, "psz and lv_f are fixed at creation (they size the camera and the pyramids)");
+  tr->op = *op;
+  return ICT_OK;
+}
+
+static int tracker_reserve(ict_tracker* tr, int T, int64_t total) {
+  CU(tr->pt_off.reserve(sizeof(int64_t) * (size_t)(T + 1)));
+  CU(tr->pt3d.reserve(sizeof(float) * 3 * (size_t)(total ? total : 1)));
+  CU(tr->norm.reserve(sizeof(double) * 4 * (size_t)T));
+  CU(tr->pt2d.reserve(sizeof(float) * 2 * (size_t)(total ? total : 1)));
+  return ICT_OK;
+}
+
+int ict_tracker_set_points(ict_tracker* tr, int T, const int64_t* pt_off, double* pts, int mutate_caller) {
+  if (!tr || T <= 0 || !pt_off || !pts) return fail(ICT_ERR_BAD_ARG, "ict_tracker_set_points: bad argument");
+  const int64_t total = pt_off[T];
+  int max_pts = 0;
+  for (int t = 0; t < T; ++t) {
+    const int64_t n = pt_off[t + 1] - pt_off[t];
+    if (n < 0 || n > 0x7fffffff) return fail(ICT_ERR_BAD_ARG, "pt_off must be non-decreasing");
+    if (n > max_pts) max_pts = (int)n;
+  }
+  if (tracker_reserve(tr, T, total)) return ICT_ERR_CUDA;
+  CU(tr->pts.reserve(sizeof(double) * 3 * (size_t)(total ? total : 1)));
+  CU(cudaMemcpyAsync(tr->pt_off.p, pt_off, sizeof(int64_t) * (size_t)(T + 1), cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(tr->pts.p, pts, sizeof(double) * 3 * (size_t)total, cudaMemcpyHostToDevice, 0));
+  const bool mut = mutate_caller && tr->op.donorm;
+  CU(launch_set_points(T, tr->pt_off.as<int64_t>(), tr->pts.as<double>(), mut ? tr->pts.as<double>() : nullptr,
+                       tr->pt3d.as<float>(), tr->norm.as<double>(), tr->op.donorm, tr->op.maxpttrack, max_pts, 0));
+  if (mut) CU(cudaMemcpy(pts, tr->pts.p, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost));
+  tr->T = T;
+  tr->total = total;
+  tr->max_pts = max_pts;
+  tr->h_off.assign(pt_off, pt_off + T + 1);
+  tr->have_2d = false;
+  return ICT_OK;
+}
+
+int ict_tracker_set_points_dev(ict_tracker* tr, int T, const int64_t* pt_off_dev, const double* pts_dev,
+                               int64_t total_pts, int max_pts, void* stream) {
+  if (!tr || T <= 0 || !pt_off_dev || !pts_dev || max_pts <= 0)
+    return fail(ICT_ERR_BAD_ARG, "ict_tracker_set_points_dev: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tracker_reserve(tr, T, total_pts)) return ICT_ERR_CUDA;
+  CU(cudaMemcpyAsync(tr->pt_off.p, pt_off_dev, sizeof(int64_t) * (size_t)(T + 1), cudaMemcpyDeviceToDevice, st));
+  CU(launch_set_points(T, tr->pt_off.as<int64_t>(), pts_dev, nullptr, tr->pt3d.as<float>(), tr->norm.as<double>(),
+                       tr->op.donorm, tr->op.maxpttrack, max_pts, st));
+  tr->T = T;
+  tr->total = total_pts;
+  tr->max_pts = max_pts;
+  tr->h_off.clear();
+  tr->have_2d = false;
+  return ICT_OK;
+}
+
+// SetPose + TrackPose for all tracks; every pointer is device memory.
+static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, const int* nf_dev, int fixed_ref,
+                      int fixed_new, const double* p_in_dev, double* p_out_dev, int* iters_dev, float* trace_dev,
+                      int trace_cap, long long* npix_dev, cudaStream_t st) {
+  if (!tr || !fs) return fail(ICT_ERR_BAD_ARG, "null tracker / frame store");
+  if (tr->T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set: call ict_tracker_set_points first");
+  if (fs->lv_f != tr->op.lv_f || fs->pad != tr->op.psz || fs->w != tr->wh[0] || fs->h != tr->wh[1])
+    return fail(ICT_ERR_BAD_ARG, "frame store does not match the tracker (need lv_f, pad == psz, w, h equal)");
+  if (!rf_dev && (fixed_ref < 0 || fixed_ref >= fs->nframes || fixed_new < 0 || fixed_new >= fs->nframes))
+    return fail(ICT_ERR_BAD_ARG, "frame index out of range");
+  TrackParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.op = tr->op;
+  prm.cam = tr->cam;
+  prm.frames = fs->desc;
+  prm.ref_frame = rf_dev;
+  prm.new_frame = nf_dev;
+  prm.fixed_ref = fixed_ref;
+  prm.fixed_new = fixed_new;
+  prm.pt_off = tr->pt_off.as<int64_t>();
+  prm.pt3d = tr->pt3d.as<float>();
+  prm.norm = tr->norm.as<double>();
+  prm.p_in = p_in_dev;
+  prm.p_out = p_out_dev;
+  prm.iters = iters_dev;
+  prm.trace = trace_dev;
+  prm.trace_cap = trace_cap;
+  prm.npixres = npix_dev;
+  prm.pt2d_out = tr->pt2d.as<float>();
+  prm.T = tr->T;
+  prm.t0 = 0;
+  const size_t smem = track_smem_bytes(tr->op, tr->max_pts);
+  if (smem <= (size_t)(227 * 1024 - 8192)) {
+    CU(launch_track(prm, tr->max_pts, st));
+  } else {
+    // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
+    if (tr->h_off.empty()) return fail(ICT_ERR_UNSUPPORTED, "big tracks need host-side pt_off (use ict_tracker_set_points)");
+    if (rf_dev) return fail(ICT_ERR_UNSUPPORTED, "big tracks take fixed ref/new frames (use ict_track_sequence or T=1)");
+    for (int t = 0; t < tr->T; ++t) {
+      const int64_t n = tr->h_off[t + 1] - tr->h_off[t];
+      const size_t wb = bigtrack_work_bytes(tr->op, n);
+      CU(tr->big.reserve(wb));
+      CU(launch_track_big(prm, t, n, tr->big.p, st));
+    }
+  }
+  tr->have_2d = true;
+  return ICT_OK;
+}
+
+int ict_track_batch_dev(ict_tracker* tr, const ict_frames* fs, const int* ref_frame_dev, const int* new_frame_dev,
+                        const double* p_in_dev, double* p_out_dev, int* iters_dev, float* trace_dev, int trace_cap,
+                        int64_t* npixres_dev, void* stream) {
+  if (!ref_frame_dev || !new_frame_dev || !p_in_dev || !p_out_dev) return fail(ICT_ERR_BAD_ARG, "null device pointer");
+  return run_tracks(tr, fs, ref_frame_dev, new_frame_dev, -1, -1, p_in_dev, p_out_dev, iters_dev, trace_dev,
+                    trace_dev ? trace_cap : 0, (long long*)npixres_dev, (cudaStream_t)stream);
+}
+
+int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame, const int* new_frame,
+                    const double* p_in, double* p_out, int* iters, float* trace, int trace_cap, int64_t* npixres) {
+  if (!tr || !fs || !ref_frame || !new_frame || !p_in || !p_out) return fail(ICT_ERR_BAD_ARG, "null argument");
+  const int T = tr->T;
+  if (T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
+  const int L = tr->op.lv_f - tr->op.lv_l + 1;
+  for (int t = 0; t < T; ++t)
+    if (ref_frame[t] < 0 || ref_frame[t] >= fs->nframes || new_frame[t] < 0 || new_frame[t] >= fs->nframes)
+      return fail(ICT_ERR_BAD_ARG, "frame index out of range");
+  CU(tr->rf.reserve(sizeof(int) * (size_t)T));
+  CU(tr->nf.reserve(sizeof(int) * (size_t)T));
+  CU(tr->p_in.reserve(sizeof(double) * 6 * (size_t)T));
+  CU(tr->p_out.reserve(sizeof(double) * 6 * (size_t)T));
+  CU(tr->iters.reserve(sizeof(int) * (size_t)T * L));
+  CU(tr->npix.reserve(sizeof(long long) * (size_t)T));
+  if (trace && trace_cap > 0) CU(tr->trace.reserve(sizeof(float) * ICT_TRACE_FLOATS * (size_t)T * trace_cap));
+  CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
+  const bool big = track_smem_bytes(tr->op, tr->max_pts) > (size_t)(227 * 1024 - 8192);
+  int rc;
+  if (big) {
+    // multi-CTA path runs one track at a time with fixed frames
+    if (T != 1) return fail(ICT_ERR_UNSUPPORTED, "tracks too large for one CTA: pass them one per call (T=1)");
+    rc = run_tracks(tr, fs, nullptr, nullptr, ref_frame[0], new_frame[0], tr->p_in.as<double>(), tr->p_out.as<double>(),
+                    tr->iters.as<int>(), trace && trace_cap > 0 ? tr->trace.as<float>() : nullptr, trace_cap,
+                    tr->npix.as<long long>(), 0);
+  } else {
+    rc = run_tracks(tr, fs, tr->rf.as<int>(), tr->nf.as<int>(), -1, -1, tr->p_in.as<double>(), tr->p_out.as<double>(),
+                    tr->iters.as<int>(), trace && trace_cap > 0 ? tr->trace.as<float>() : nullptr, trace_cap,
+                    tr->npix.as<long long>(), 0);
+  }
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(p_out, tr->p_out.p, sizeof(double) * 6 * (size_t)T, cudaMemcpyDeviceToHost, 0));
+  if (iters) CU(cudaMemcpyAsync(iters, tr->iters.p, sizeof(int) * (size_t)T * L, cudaMemcpyDeviceToHost, 0));
+  if (npixres) CU(cudaMemcpyAsync(npixres, tr->npix.p, sizeof(long long) * (size_t)T, cudaMemcpyDeviceToHost, 0));
+  if (trace && trace_cap > 0)
+    CU(cudaMemcpyAsync(trace, tr->trace.p, sizeof(float) * ICT_TRACE_FLOATS * (size_t)T * trace_cap,
+                       cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  return ICT_OK;
+}
+
+int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nsteps, int step, const double* p_in,
+                       double* poses_out, int* iters, int64_t* npixres) {
+  if (!tr || !fs || !p_in || !poses_out || nsteps < 0 || (step != 1 && step != -1))
+    return fail(ICT_ERR_BAD_ARG, "ict_track_sequence: bad argument");
+  const int T = tr->T;
+  if (T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
+  const int L = tr->op.lv_f - tr->op.lv_l + 1;
+  const int last = first + nsteps * step;
+  if (first < 0 || first >= fs->nframes || last < 0 || last >= fs->nframes)
+    return fail(ICT_ERR_BAD_ARG, "frame range out of bounds");
+  // all poses of the chain live on the device: the output of step k is the input of step k+1
+  CU(tr->p_out.reserve(sizeof(double) * 6 * (size_t)T * (nsteps + 1)));
+  CU(tr->iters.reserve(sizeof(int) * (size_t)T * L * (nsteps ? nsteps : 1)));
+  CU(tr->npix.reserve(sizeof(long long) * (size_t)T * (nsteps ? nsteps : 1)));
+  double* chain = tr->p_out.as<double>();
+  CU(cudaMemcpyAsync(chain, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
+  for (int k = 0; k < nsteps; ++k) {
+    const int fr = first + k * step;
+    int rc = run_tracks(tr, fs, nullptr, nullptr, fr, fr + step, chain + (size_t)k * 6 * T,
+                        chain + (size_t)(k + 1) * 6 * T, tr->iters.as<int>() + (size_t)k * T * L, nullptr, 0,
+                        tr->npix.as<long long>() + (size_t)k * T, 0);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(poses_out, chain, sizeof(double) * 6 * (size_t)T * (nsteps + 1), cudaMemcpyDeviceToHost, 0));
+  if (iters && nsteps)
+    CU(cudaMemcpyAsync(iters, tr->iters.p, sizeof(int) * (size_t)T * L * nsteps, cudaMemcpyDeviceToHost, 0));
+  if (npixres && nsteps)
+    CU(cudaMemcpyAsync(npixres, tr->npix.p, sizeof(long long) * (size_t)T * nsteps, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  return ICT_OK;
+}
+
+int ict_tracker_get_2dpoints(ict_tracker* tr, float* out) {
+  if (!tr || !out) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (!tr->have_2d) return fail(ICT_ERR_BAD_ARG, "no SetPose has run yet");
+  CU(cudaMemcpy(out, tr->pt2d.p, sizeof(float) * 2 * (size_t)tr->total, cudaMemcpyDeviceToHost));
+  return ICT_OK;
+}
+
+int ict_track_pair(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2], const float* imgA,
+                   const float* imgB, double* pt3d, int npts, const double p_in[6], double p_out[6], int* iters,
+                   float* trace, int trace_cap) {
+  if (require_device()) return ICT_ERR_NO_DEVICE;
+  if (!op || !imgA || !imgB || !pt3d || npts <= 0) return fail(ICT_ERR_BAD_ARG, "ict_track_pair: bad argument");
+  ict_frames* fs = ict_frames_create(2, wh[0], wh[1], op->lv_f, op->psz);
+  if (!fs) return ICT_ERR_BAD_ARG;
+  ict_tracker* tr = ict_tracker_create(op, fc, cc, wh);
+  int rc = tr ? ICT_OK : ICT_ERR_BAD_ARG;
+  if (rc == ICT_OK) rc = ict_frames_upload(fs, 0, 1, imgA);
+  if (rc == ICT_OK) rc = ict_frames_upload(fs, 1, 1, imgB);
+  const int64_t off[2] = {0, npts};
+  if (rc == ICT_OK) rc = ict_tracker_set_points(tr, 1, off, pt3d, 1);
+  const int rf = 0, nf = 1;
+  if (rc == ICT_OK) rc = ict_track_batch(tr, fs, &rf, &nf, p_in, p_out, iters, trace, trace_cap, nullptr);
+  ict_tracker_destroy(tr);
+  ict_frames_destroy(fs);
+  return rc;
+}
+
+int ict_ncc_score(ict_tracker* tr, const ict_frames* fs, int frame_b, int frame_r, int frame_f, int nback, int nfwd,
+                  const float* pt2d_back, const float* pt2d_refe, const float* pt2d_forw, float* out_corr) {
+  if (!tr || !fs || !pt2d_back || !pt2d_refe || !pt2d_forw || !out_corr) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (tr->T <= 0 || tr->h_off.empty()) return fail(ICT_ERR_BAD_ARG, "no points set");
+  if (frames_range_ok(fs, frame_b, 1) || frames_range_ok(fs, frame_r, 1) || frames_range_ok(fs, frame_f, 1))
+    return ICT_ERR_BAD_ARG;
+  const size_t total = (size_t)tr->total;
+  DevBuf in, out;
+  CU(in.reserve(sizeof(float) * 6 * total));
+  CU(out.reserve(sizeof(float) * total));
+  float* d = in.as<float>();
+  CU(cudaMemcpyAsync(d, pt2d_back, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(d + 2 * total, pt2d_refe, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(d + 4 * total, pt2d_forw, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
+  const int l = tr->op.lv_l;
+  const size_t fo = (size_t)fs->plane_floats;
+  cudaError_t e = launch_ncc(tr->op, tr->cam, fs->I + frame_b * fo + fs->level_off[l], fs->I + frame_r * fo + fs->level_off[l],
+                             fs->I + frame_f * fo + fs->level_off[l], nback, nfwd, tr->pt_off.as<int64_t>(), tr->T, d,
+                             d + 2 * total, d + 4 * total, out.as<float>(), 0);
+  int rc = ICT_OK;
+  if (e != cudaSuccess) rc = fail(ICT_ERR_CUDA, std::string("launch_ncc: ") + cudaGetErrorString(e));
+  if (rc == ICT_OK && cudaMemcpy(out_corr, out.p, sizeof(float) * total, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(ICT_ERR_CUDA, "ncc download failed");
+  in.release();
+  out.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// ict_device.cuh — device-side scalar pieces of the tracking path (sm_100a).
+//
+// Everything here is small, per-track (not per-pixel) arithmetic whose ORDER OF OPERATIONS follows the reference
+// line by line so that the GPU result matches the reference's fp32/fp64 mix.  The translation unit is compiled
+// with -fmad=false: no multiply-add is ever contracted, as in the reference's -msse4 -mavx (no -mfma) build
+// (CMakeLists.txt:4).  Division and sqrt are IEEE (nvcc defaults -prec-div=true -prec-sqrt=true, no fast-math).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ICT_LIEALG_SIGTHRESH 1e-4   /* utilities.h:22 */
+#define ICT_LIEALG_EPSILON 1e-10    /* utilities.h:23 */
+
+namespace ict {
+
+// ---- util_SE3_coeff_to_group<T>, utilities.h:84-145 ---------------------------------------------------------
+// T=float: the template's unqualified sqrt/sin/cos bind to the double C functions, so those sub-expressions are
+// evaluated in double and narrowed on assignment (see oracle/ictrack_oracle.c, DEF_SE3_EXP).
+template <typename T>
+__device__ __forceinline__ void se3_exp(T* G, const T* p) {
+  T ra1 = p[3] * p[3];
+  T ra2 = p[4] * p[4];
+  T ra3 = p[5] * p[5];
+  T sig = (T)sqrt((double)(T)(ra1 + ra2 + ra3));
+  T sa, sb, sc;
+  T sigsq2 = (sig * sig);
+  T sigsq3 = (sig * sig * sig);
+  if ((double)sig > ICT_LIEALG_SIGTHRESH) {
+    double sn, cs;
+    sincos((double)sig, &sn, &cs);
+    sa = (T)(sn / (double)sig);
+    sb = (T)((1 - cs) / (double)sigsq2);
+    sc = (T)(((double)sig - sn) / (double)sigsq3);
+  } else {
+    sa = 1 - sigsq2 / 6 * (1 - sigsq2 / 20 * (1 - sigsq2 / 42));
+    sb = (T)(.5 * (double)(T)(1 - sigsq2 / 12 * (1 - sigsq2 / 30 * (1 - sigsq2 / 56))));
+    sc = (1 - sigsq2 / 20 * (1 - sigsq2 / 42 * (1 - sigsq2 / 72))) / 6;
+  }
+  T tmp1 = ra2 * sb;
+  T tmp2 = ra3 * sb;
+  T tmp3 = ra1 * sb;
+  T tmp4 = p[3] * p[4] * sb;
+  T tmp5 = p[5] * sa;
+  T tmp6 = p[3] * p[5] * sb;
+  T tmp7 = p[4] * sa;
+  T tmp8 = p[3] * sa;
+  T tmp9 = p[4] * p[5] * sb;
+  G[0] = 1 - tmp1 - tmp2;
+  G[1] = tmp4 - tmp5;
+  G[2] = tmp7 + tmp6;
+  G[4] = tmp5 + tmp4;
+  G[5] = 1 - tmp3 - tmp2;
+  G[6] = tmp9 - tmp8;
+  G[8] = tmp6 - tmp7;
+  G[9] = tmp8 + tmp9;
+  G[10] = 1 - tmp3 - tmp1;
+  tmp1 = p[5] * sb;
+  tmp2 = p[3] * p[4] * sc;
+  tmp3 = p[4] * sb;
+  tmp4 = p[3] * p[5] * sc;
+  tmp5 = p[3] * sb;
+  tmp6 = p[4] * p[5] * sc;
+  G[3] = (1 - (ra2 + ra3) * sc) * p[0] + (tmp2 - tmp1) * p[1] + (tmp3 + tmp4) * p[2];
+  G[7] = (tmp1 + tmp2) * p[0] + (1 - (ra1 + ra3) * sc) * p[1] + (tmp6 - tmp5) * p[2];
+  G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
+}
+
+// ---- util_SE3_group_to_coeff<T>, utilities.h:149-241 --------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void se3_log(T* p, const T* G) {
+  T trace = G[0] + G[5] + G[10];
+  T theta = (T)acos((double)(T)(0.5f * (trace - 1)));
+  T oh[9], ohs[9], V[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { oh[k] = 0; ohs[k] = 0; }
+  if ((double)theta < ICT_LIEALG_EPSILON) {
+    p[3] = 0.0f;
+    p[4] = 0.0f;
+    p[5] = 0.0f;
+  } else {
+    T coef = (T)((double)theta / ((double)2.0f * sin((double)theta)));
+    oh[1] = coef * (G[1] - G[4]);
+    oh[3] = -oh[1];
+    oh[2] = coef * (G[2] - G[8]);
+    oh[6] = -oh[2];
+    oh[5] = coef * (G[6] - G[9]);
+    oh[7] = -oh[5];
+    p[3] = -oh[5];
+    p[4] = oh[2];
+    p[5] = -oh[1];
+    T omsq1 = oh[1] * oh[1];
+    T omsq2 = oh[2] * oh[2];
+    T omsq3 = oh[5] * oh[5];
+    ohs[0] = -omsq1 - omsq2;
+    ohs[1] = -oh[2] * oh[5];
+    ohs[3] = ohs[1];
+    ohs[2] = oh[1] * oh[5];
+    ohs[6] = ohs[2];
+    ohs[4] = -omsq1 - omsq3;
+    ohs[5] = -oh[1] * oh[2];
+    ohs[7] = ohs[5];
+    ohs[8] = -omsq2 - omsq3;
+  }
+  T th;
+  if ((double)theta < ICT_LIEALG_SIGTHRESH)
+    th = 1.0f / 12.0f;
+  else
+    th = (T)(((double)1.0f - (double)theta / ((double)2.0f * tan((double)(T)(theta / 2.0f)))) /
+             (double)(T)(theta * theta));
+  V[0] = 1.0f + th * ohs[0];
+  V[1] = -0.5f * oh[1] + th * ohs[1];
+  V[2] = -0.5f * oh[2] + th * ohs[2];
+  V[3] = -0.5f * oh[3] + th * ohs[3];
+  V[4] = 1.0f + th * ohs[4];
+  V[5] = -0.5f * oh[5] + th * ohs[5];
+  V[6] = -0.5f * oh[6] + th * ohs[6];
+  V[7] = -0.5f * oh[7] + th * ohs[7];
+  V[8] = 1.0f + th * ohs[8];
+  p[0] = V[0] * G[3] + V[1] * G[7] + V[2] * G[11];
+  p[1] = V[3] * G[3] + V[4] * G[7] + V[5] * G[11];
+  p[2] = V[6] * G[3] + V[7] * G[7] + V[8] * G[11];
+}
+
+// ---- PoseClass::setpose_se3, pose.cpp:25-76 -------------------------------------------------------------------
+static __device__ __noinline__ void setpose_se3(const double* p_in, bool donorm, const double* meanshift, double varval,
+                                   float* cpos_p, float* cpos_G) {
+  double p[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p[k] = p_in[k];
+  if (donorm) {
+    double G[12], t[3];
+    se3_exp<double>(G, p);
+    t[0] = -G[0] * G[3] - G[4] * G[7] - G[8] * G[11];
+    t[1] = -G[1] * G[3] - G[5] * G[7] - G[9] * G[11];
+    t[2] = -G[2] * G[3] - G[6] * G[7] - G[10] * G[11];
+    t[0] = (t[0] - meanshift[0]) / varval;
+    t[1] = (t[1] - meanshift[1]) / varval;
+    t[2] = (t[2] - meanshift[2]) / varval;
+    G[3] = -G[0] * t[0] - G[1] * t[1] - G[2] * t[2];
+    G[7] = -G[4] * t[0] - G[5] * t[1] - G[6] * t[2];
+    G[11] = -G[8] * t[0] - G[9] * t[1] - G[10] * t[2];
+    se3_log<double>(p, G);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cpos_p[k] = (float)p[k];
+  se3_exp<float>(cpos_G, cpos_p);
+}
+
+// ---- PoseClass::getPose_se3, pose.cpp:79-113 ------------------------------------------------------------------
+static __device__ __noinline__ void getpose_se3(const float* cpos_p, const float* cpos_G, bool donorm, const double* meanshift,
+                                   double varval, double* p_out) {
+  float pu[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) pu[k] = cpos_p[k];
+  if (donorm) {
+    float G[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) G[k] = cpos_G[k];
+    double t[3];
+    t[0] = (double)(-G[0] * G[3] - G[4] * G[7] - G[8] * G[11]);   // fp32 expression widened on assignment
+    t[1] = (double)(-G[1] * G[3] - G[5] * G[7] - G[9] * G[11]);
+    t[2] = (double)(-G[2] * G[3] - G[6] * G[7] - G[10] * G[11]);
+    t[0] = t[0] * varval + meanshift[0];
+    t[1] = t[1] * varval + meanshift[1];
+    t[2] = t[2] * varval + meanshift[2];
+    G[3] = (float)(-(double)G[0] * t[0] - (double)G[1] * t[1] - (double)G[2] * t[2]);
+    G[7] = (float)(-(double)G[4] * t[0] - (double)G[5] * t[1] - (double)G[6] * t[2]);
+    G[11] = (float)(-(double)G[8] * t[0] - (double)G[9] * t[1] - (double)G[10] * t[2]);
+    se3_log<float>(pu, G);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p_out[k] = (double)pu[k];
+}
+
+// ---- Hes.fullPivLu() (odometer.cpp:514), factor once per level; same elimination order as Eigen 3.3 ----------
+struct Lu6 {
+  float lu[36];   // column-major
+  int rowtr[6], coltr[6];
+  int rank;
+};
+
+static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  for (int k = 0; k < 36; ++k) f.lu[k] = H[k];
+  int nonzero = 6;
+  float maxpivot = 0.0f;
+  for (int k = 0; k < 6; ++k) {
+    int pr = k, pc = k;
+    float biggest = -1.0f;
+    for (int j = k; j < 6; ++j)
+      for (int i = k; i < 6; ++i) {
+        float v = fabsf(LU(i, j));
+        if (v > biggest) { biggest = v; pr = i; pc = j; }
+      }
+    if (biggest == 0.0f) {
+      nonzero = k;
+      for (int i = k; i < 6; ++i) { f.rowtr[i] = i; f.coltr[i] = i; }
+      break;
+    }
+    if (biggest > maxpivot) maxpivot = biggest;
+    f.rowtr[k] = pr;
+    f.coltr[k] = pc;
+    if (k != pr) for (int j = 0; j < 6; ++j) { float t = LU(k, j); LU(k, j) = LU(pr, j); LU(pr, j) = t; }
+    if (k != pc) for (int i = 0; i < 6; ++i) { float t = LU(i, k); LU(i, k) = LU(i, pc); LU(i, pc) = t; }
+    if (k < 5) {
+      for (int i = k + 1; i < 6; ++i) LU(i, k) = LU(i, k) / LU(k, k);
+      for (int j = k + 1; j < 6; ++j)
+        for (int i = k + 1; i < 6; ++i) LU(i, j) = LU(i, j) - LU(i, k) * LU(k, j);
+    }
+  }
+  const float premult = fabsf(maxpivot) * (1.1920929e-07f * 6.0f);
+  int rank = 0;
+  for (int i = 0; i < nonzero; ++i) rank += (fabsf(LU(i, i)) > premult);
+  f.rank = rank;
+#undef LU
+}
+
+static __device__ __noinline__ void lu6_solve(const Lu6& f, const float* b, float* x) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  if (f.rank == 0) {
+    for (int i = 0; i < 6; ++i) x[i] = 0.0f;
+    return;
+  }
+  float c[6];
+  for (int i = 0; i < 6; ++i) c[i] = b[i];
+  for (int k = 0; k < 6; ++k)
+    if (f.rowtr[k] != k) { float t = c[k]; c[k] = c[f.rowtr[k]]; c[f.rowtr[k]] = t; }
+  for (int i = 0; i < 6; ++i)
+    for (int r = i + 1; r < 6; ++r) c[r] = c[r] - c[i] * LU(r, i);
+  for (int i = f.rank - 1; i >= 0; --i) {
+    c[i] = c[i] / LU(i, i);
+    for (int r = 0; r < i; ++r) c[r] = c[r] - c[i] * LU(r, i);
+  }
+  for (int i = f.rank; i < 6; ++i) c[i] = 0.0f;
+  for (int k = 5; k >= 0; --k)
+    if (f.coltr[k] != k) { float t = c[k]; c[k] = c[f.coltr[k]]; c[f.coltr[k]] = t; }
+  for (int i = 0; i < 6; ++i) x[i] = c[i];
+#undef LU
+}
+
+// ---- bilinear patch placement, util_getPatch / util_getPatch_grad (utilities.cpp:65-94, 127-157) -----------------
+// For a patch centre `mid` returns the flat offset of the patch's first pixel (row pos1+pszd2, col pos0+pszd2 of
+// the padded plane) and the four constant weights.
+struct PatchPlace {
+  int base;
+  float w0, w1, w2, w3;
+};
+__device__ __forceinline__ PatchPlace patch_place(float mx, float my, int pszd2, int width) {
+  PatchPlace q;
+  const int pos0 = (int)ceilf(mx + .00001f);
+  const int pos1 = (int)ceilf(my + .00001f);
+  const int pos2 = (int)floorf(mx);
+  const int pos3 = (int)floorf(my);
+  const float r0 = mx - (float)pos2;
+  const float r1 = my - (float)pos3;
+  q.w0 = r0 * r1;
+  q.w1 = (1 - r0) * r1;
+  q.w2 = r0 * (1 - r1);
+  q.w3 = (1 - r0) * (1 - r1);
+  q.base = (pos1 + pszd2) * width + pos0 + pszd2;
+  return q;
+}
+
+// we[0]*a + we[1]*b + we[2]*c + we[3]*d, left to right (utilities.cpp:107,181-183)
+__device__ __forceinline__ float bilin4(const float* __restrict__ img, int addr, int width, float w0, float w1,
+                                        float w2, float w3) {
+  const float a = __ldg(img + addr);
+  const float b = __ldg(img + addr - 1);
+  const float c = __ldg(img + addr - width);
+  const float d = __ldg(img + addr - width - 1);
+  return ((w0 * a + w1 * b) + w2 * c) + w3 * d;
+}
+
+// ---- per-point steepest-descent coefficients, odometer.cpp:306-326 ---------------------------------------------
+// sd1 = dx*c[0]; sd2 = dy*c[1]; sd3 = dx*c[2]+dy*c[3]; sd4 = dx*c[4]+dy*c[5]; sd5 = dx*c[6]+dy*c[7];
+// sd6 = dx*c[8]+dy*c[9].  The two "1.0 + ..." terms are double in the reference and narrowed by Eigen's scalar op.
+__device__ __forceinline__ void sd_coefs(float pt_x, float pt_y, float pt_z, float fx, float fy, float* c) {
+  const float pt_zsq = pt_z * pt_z;
+  c[0] = (fx / pt_z);
+  c[1] = (fy / pt_z);
+  c[2] = (-pt_x / pt_zsq * fx);
+  c[3] = (-pt_y / pt_zsq * fy);
+  c[4] = (-pt_x * pt_y / pt_zsq * fx);
+  c[5] = (float)((-(1.0 + (double)(pt_y * pt_y / pt_zsq))) * (double)fy);
+  c[6] = (float)((1.0 + (double)(pt_x * pt_x / pt_zsq)) * (double)fx);
+  c[7] = (pt_x * pt_y / pt_zsq * fy);
+  c[8] = (-pt_y / pt_z * fx);
+  c[9] = (pt_x / pt_z * fy);
+}
+
+__device__ __forceinline__ void sd_values(float gx, float gy, const float* c, float* sd) {
+  sd[0] = gx * c[0];
+  sd[1] = gy * c[1];
+  sd[2] = gx * c[2] + gy * c[3];
+  sd[3] = gx * c[4] + gy * c[5];
+  sd[4] = gx * c[6] + gy * c[7];
+  sd[5] = gx * c[8] + gy * c[9];
+}
+
+// deterministic warp tree (fixed order, no atomics on floats)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ict

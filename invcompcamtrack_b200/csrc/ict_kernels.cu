@@ -1,0 +1,606 @@
+// ict_kernels.cu — hand-written sm_100a kernels of the inverse-compositional GN tracking path.
+//
+//   K0  k_pyr_level0 / k_pyr_levelN   util_constructpyramide        utilities.cpp:14-52
+//   K1a k_set_points                  OdometerClass::Set3Dpoints    odometer.cpp:171-239
+//   K2  k_track<PSZ,PN>               SetPose + TrackPose           odometer.cpp:241-426, pose.cpp, utilities.cpp:55-189
+//
+// Compiled with -fmad=false (see ict_device.cuh).  No tensor cores: the loop is a gather + streaming
+// reduction (about 0.6 flop/B), see DESIGN.md.
+#include "ict_kernels.cuh"
+#include "ict_device.cuh"
+
+#include <atomic>
+
+namespace ict {
+
+static std::atomic<long long> g_launches{0};
+int64_t launch_count(int reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+#define COUNT_LAUNCH() g_launches.fetch_add(1)
+void count_launch_external() { g_launches.fetch_add(1); }
+
+// ==================================================================================================
+// K0 — pyramid: per level one launch over the PADDED output plane of every frame in the batch.
+//   level 0   : v = src                                    (clone + convertTo CV_32F, utilities.cpp:21,26)
+//   level l>0 : v = ((a+b)+(c+d))*0.25 of level l-1        (cv::resize 1/2 INTER_LINEAR == area-fast, :24)
+//   dx = v(x+1)-v(x-1), dy = v(y+1)-v(y-1), 0 on the first/last col/row (Sobel ksize 1, REFLECT_101, :30-31)
+//   padding: replicate for I (:40), zero for dx/dy (:45-46)
+// Each thread produces one padded output pixel; neighbouring values are re-read through L1/L2 (the whole
+// level is a few MB).  Pure HBM streaming: 4 B read + 12 B written per padded pixel at level 0.
+// ==================================================================================================
+template <typename SrcT>
+__global__ void __launch_bounds__(256) k_pyr_level0(const SrcT* __restrict__ src, int w, int h, int pad,
+                                                    float* __restrict__ I, float* __restrict__ dx,
+                                                    float* __restrict__ dy, int64_t plane_stride) {
+  const int sw = w + 2 * pad, sh = h + 2 * pad;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (X >= sw || Y >= sh) return;
+  const SrcT* s = src + (int64_t)blockIdx.z * w * h;
+  const int x = X - pad, y = Y - pad;
+  const int xc = min(max(x, 0), w - 1), yc = min(max(y, 0), h - 1);
+  const float v = (float)s[(int64_t)yc * w + xc];
+  const bool inside = (x >= 0) & (x < w) & (y >= 0) & (y < h);
+  float gx = 0.0f, gy = 0.0f;
+  if (inside) {
+    if (x > 0 && x < w - 1) gx = (float)s[(int64_t)y * w + x + 1] - (float)s[(int64_t)y * w + x - 1];
+    if (y > 0 && y < h - 1) gy = (float)s[(int64_t)(y + 1) * w + x] - (float)s[(int64_t)(y - 1) * w + x];
+  }
+  const int64_t o = (int64_t)blockIdx.z * plane_stride + (int64_t)Y * sw + X;
+  I[o] = v;
+  dx[o] = gx;
+  dy[o] = gy;
+}
+
+__device__ __forceinline__ float mean4(const float* __restrict__ Ip, int swp, int pad, int x, int y) {
+  const float* r0 = Ip + (int64_t)(2 * y + pad) * swp + 2 * x + pad;
+  const float2 a = make_float2(__ldg(r0), __ldg(r0 + 1));
+  const float2 c = make_float2(__ldg(r0 + swp), __ldg(r0 + swp + 1));
+  return ((a.x + a.y) + (c.x + c.y)) * 0.25f;
+}
+
+__global__ void __launch_bounds__(256) k_pyr_levelN(float* __restrict__ I, float* __restrict__ dx,
+                                                    float* __restrict__ dy, int64_t plane_stride, int64_t off_prev,
+                                                    int swp, int64_t off_cur, int lw, int lh, int pad) {
+  const int sw = lw + 2 * pad, sh = lh + 2 * pad;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (X >= sw || Y >= sh) return;
+  const float* Ip = I + (int64_t)blockIdx.z * plane_stride + off_prev;
+  const int x = X - pad, y = Y - pad;
+  const int xc = min(max(x, 0), lw - 1), yc = min(max(y, 0), lh - 1);
+  const float v = mean4(Ip, swp, pad, xc, yc);
+  const bool inside = (x >= 0) & (x < lw) & (y >= 0) & (y < lh);
+  float gx = 0.0f, gy = 0.0f;
+  if (inside) {
+    if (x > 0 && x < lw - 1) gx = mean4(Ip, swp, pad, x + 1, y) - mean4(Ip, swp, pad, x - 1, y);
+    if (y > 0 && y < lh - 1) gy = mean4(Ip, swp, pad, x, y + 1) - mean4(Ip, swp, pad, x, y - 1);
+  }
+  const int64_t o = (int64_t)blockIdx.z * plane_stride + off_cur + (int64_t)Y * sw + X;
+  I[o] = v;
+  dx[o] = gx;
+  dy[o] = gy;
+}
+
+cudaError_t launch_pyramid(const float* src_f32, const unsigned char* src_u8, int count, int w, int h, int lv_f,
+                           int pad, float* I, float* dx, float* dy, int64_t plane_floats,
+                           const int64_t* level_off, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const dim3 blk(32, 8, 1);
+  for (int z0 = 0; z0 < count; z0 += 65535) {
+    const int zc = min(count - z0, 65535);
+    float* Iz = I + (int64_t)z0 * plane_floats;
+    float* dxz = dx + (int64_t)z0 * plane_floats;
+    float* dyz = dy + (int64_t)z0 * plane_floats;
+    {
+      const int sw = w + 2 * pad, sh = h + 2 * pad;
+      const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
+      if (src_u8)
+        k_pyr_level0<unsigned char><<<grd, blk, 0, stream>>>(src_u8 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                              plane_floats);
+      else
+        k_pyr_level0<float><<<grd, blk, 0, stream>>>(src_f32 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                      plane_floats);
+      COUNT_LAUNCH();
+    }
+    for (int l = 1; l <= lv_f; ++l) {
+      const int lw = w >> l, lh = h >> l;
+      const int sw = lw + 2 * pad, sh = lh + 2 * pad;
+      const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
+      k_pyr_levelN<<<grd, blk, 0, stream>>>(Iz, dxz, dyz, plane_floats, level_off[l - 1], (w >> (l - 1)) + 2 * pad,
+                                            level_off[l], lw, lh, pad);
+      COUNT_LAUNCH();
+    }
+  }
+  return cudaGetLastError();
+}
+
+// ==================================================================================================
+// K1a — Set3Dpoints (odometer.cpp:171-239): optional centring / division by the mean squared norm in
+// fp64, then double -> float.  One CTA per track.  The fp64 sums run in the reference's sequential
+// order on one thread for tracks up to SEQ_LIMIT points; longer tracks (dense alignment) use a fixed
+// two-stage tree (fp64, so the difference is ~1e-16 relative and vanishes in the float cast).
+// ==================================================================================================
+#define ICT_SEQ_LIMIT 8192
+
+__global__ void __launch_bounds__(256) k_set_points(int T, const int64_t* __restrict__ pt_off,
+                                                    const double* pts, double* pts_mut,
+                                                    float* __restrict__ pt3d, double* __restrict__ norm,
+                                                    int donorm, int maxpttrack) {
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  const int64_t off = pt_off[t];
+  const int n_in = (int)(pt_off[t + 1] - off);
+  const int P = min(n_in, maxpttrack);
+  const double* p1 = pts + 3 * off;
+  const double* p2 = p1 + n_in;
+  const double* p3 = p2 + n_in;
+  float* q1 = pt3d + 3 * off;
+  float* q2 = q1 + n_in;
+  float* q3 = q2 + n_in;
+  __shared__ double s_norm[4];
+  __shared__ double s_red[3][8];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (!donorm) {
+    for (int i = tid; i < P; i += nt) {
+      q1[i] = (float)p1[i];
+      q2[i] = (float)p2[i];
+      q3[i] = (float)p3[i];
+    }
+    if (tid < 4) norm[4 * (int64_t)t + tid] = 0.0;
+    return;
+  }
+  if (P <= ICT_SEQ_LIMIT) {
+    if (tid == 0) {
+      const double nd = (double)P;
+      double m0 = 0, m1 = 0, m2 = 0, var = 0;
+      for (int i = 0; i < P; ++i) m0 += p1[i];
+      for (int i = 0; i < P; ++i) m1 += p2[i];
+      for (int i = 0; i < P; ++i) m2 += p3[i];
+      m0 /= nd;
+      m1 /= nd;
+      m2 /= nd;
+      for (int i = 0; i < P; ++i) {
+        const double a = p1[i] - m0, b = p2[i] - m1, c = p3[i] - m2;
+        var += a * a + b * b + c * c;
+      }
+      var /= nd;
+      s_norm[0] = m0; s_norm[1] = m1; s_norm[2] = m2; s_norm[3] = var;
+    }
+  } else {
+    // fixed-order tree: per-thread strided partials -> warp shuffle -> 8 warps
+    double a[3] = {0, 0, 0};
+    for (int i = tid; i < P; i += nt) { a[0] += p1[i]; a[1] += p2[i]; a[2] += p3[i]; }
+    for (int k = 0; k < 3; ++k) {
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], o);
+      if ((tid & 31) == 0) s_red[k][tid >> 5] = a[k];
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int k = 0; k < 3; ++k) {
+        double s = 0;
+        for (int wv = 0; wv < (nt >> 5); ++wv) s += s_red[k][wv];
+        s_norm[k] = s / (double)P;
+      }
+    __syncthreads();
+    double v = 0;
+    for (int i = tid; i < P; i += nt) {
+      const double x = p1[i] - s_norm[0], y = p2[i] - s_norm[1], z = p3[i] - s_norm[2];
+      v += x * x + y * y + z * z;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[0][tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0;
+      for (int wv = 0; wv < (nt >> 5); ++wv) s += s_red[0][wv];
+      s_norm[3] = s / (double)P;
+    }
+  }
+  __syncthreads();
+  const double m0 = s_norm[0], m1 = s_norm[1], m2 = s_norm[2], var = s_norm[3];
+  for (int i = tid; i < P; i += nt) {
+    const double a = p1[i] - m0, b = p2[i] - m1, c = p3[i] - m2;
+    q1[i] = (float)(a / var);
+    q2[i] = (float)(b / var);
+    q3[i] = (float)(c / var);
+    if (pts_mut) {   // the reference centres the caller's array in place (odometer.cpp:207-212)
+      pts_mut[3 * off + i] = a;
+      pts_mut[3 * off + n_in + i] = b;
+      pts_mut[3 * off + 2 * (int64_t)n_in + i] = c;
+    }
+  }
+  if (tid < 4) norm[4 * (int64_t)t + tid] = s_norm[tid];
+}
+
+cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, double* pts_mut, float* pt3d,
+                              double* norm, int donorm, int maxpttrack, int max_pts, cudaStream_t stream) {
+  (void)max_pts;
+  if (T <= 0) return cudaSuccess;
+  k_set_points<<<T, 256, 0, stream>>>(T, pt_off, pts, pts_mut, pt3d, norm, donorm, maxpttrack);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// ==================================================================================================
+// K2 — SetPose + TrackPose, one CTA per track, all levels and iterations on device.
+//
+// Shared-memory residency: for every template pixel the CTA keeps (pat_ref, pat_dx, pat_dy) = 12 B
+// in shared memory for the whole level; the six steepest-descent values are RECOMPUTED per iteration
+// from (dx,dy) and ten per-point coefficients with exactly the reference's roundings
+// (sd = fl(fl(dx*a)+fl(dy*b)), odometer.cpp:317-326), so they are bit-identical to the reference's
+// stored sd arrays while cutting the per-pixel state from 28 B to 12 B.  The new frame is gathered
+// with four read-only loads per pixel (weights constant per patch, utilities.cpp:65-76).
+//
+// Reference quirks preserved: ceil(x+1e-5f) placement, centre-only inclusive bounds
+// test, stale template/SD of points that leave the reference image at a finer level (state is only
+// zeroed at Set3Dpoints), new-frame-invisible points dropping out of J^T r but staying in H, min two
+// iterations per level, additive se(3) update, intensity-only patch mean subtraction.
+// ==================================================================================================
+struct TrackShared {
+  float G[12];
+  float p[6];
+  float Hsum[21];
+  float part[32 * 21];
+  Lu6 lu;
+  float normdp, normdp_init;
+  int cont, it, nvis;
+  long long npix;
+};
+
+template <int PSZ>
+__device__ __forceinline__ void elem_split(int e, int n, int psz, int& i, int& r, int& c) {
+  if constexpr (PSZ > 0) {
+    i = e / (PSZ * PSZ);
+    const int rem = e - i * (PSZ * PSZ);
+    r = rem / PSZ;
+    c = rem - r * PSZ;
+  } else {
+    i = e / n;
+    const int rem = e - i * n;
+    r = rem / psz;
+    c = rem - r * psz;
+  }
+}
+
+// mean of each visible patch of `buf` (n values per patch) -> s_mean[i]; one warp per patch, fixed order
+__device__ __forceinline__ void patch_means(const float* buf, float* s_mean, const int* s_vis, int visbit, int P,
+                                            int n, int warp, int lane, int nw) {
+  for (int i = warp; i < P; i += nw) {
+    if (!(s_vis[i] & visbit)) continue;
+    float s = 0.0f;
+    for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
+    s = warp_sum(s);
+    if (lane == 0) s_mean[i] = s / n;   // tmp.sum() / op->novals, utilities.cpp:112,188
+  }
+}
+
+template <int PSZ, bool PN>
+__global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ TrackShared S;
+
+  const int t = blockIdx.x + prm.t0;
+  const ict_optparam& op = prm.op;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int psz = PSZ > 0 ? PSZ : op.psz;
+  const int n = PSZ > 0 ? PSZ * PSZ : op.novals;
+  const int pszd2 = op.pszd2;
+  const int64_t off = prm.pt_off[t];
+  const int n_in = (int)(prm.pt_off[t + 1] - off);
+  const int P = min(n_in, op.maxpttrack);
+  const int E = P * n;
+  const int Epad = (E + 3) & ~3;
+  const bool donorm = op.donorm != 0;
+  const bool patchnorm = PN && (op.dopatchnorm != 0);
+
+  // ---- shared-memory carve-up ---------------------------------------------------------------------
+  float* s_ref = smem;
+  float* s_gx = s_ref + Epad;
+  float* s_gy = s_gx + Epad;
+  float* s_new = s_gy + Epad;                       // only when PN
+  float* s_ptf = PN ? s_new + Epad : s_new;         // per-point floats
+  float* s_X = s_ptf;
+  float* s_Y = s_X + P;
+  float* s_Z = s_Y + P;
+  float* s_Xc = s_Z + P;
+  float* s_Yc = s_Xc + P;
+  float* s_Zc = s_Yc + P;
+  float* s_coef = s_Zc + P;                         // [10][P]
+  float* s_w = s_coef + 10 * P;                     // [4][P]
+  float* s_mean = s_w + 4 * P;                      // [P]
+  int* s_base = (int*)(s_mean + P);                 // [P]
+  int* s_vis = s_base + P;                          // [P] bit0: visible in ref (this level), bit1: in new
+
+  const int rf = prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref;
+  const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
+  const FrameDesc* fr_ref = prm.frames + rf;
+  const FrameDesc* fr_new = prm.frames + nf;
+
+  // ---- ResetOdometer (odometer.cpp:580-609) + load float points ------------------------------------
+  for (int e = tid; e < Epad; e += nt) { s_ref[e] = 0.0f; s_gx[e] = 0.0f; s_gy[e] = 0.0f; }
+  {
+    const float* q = prm.pt3d + 3 * off;
+    for (int i = tid; i < P; i += nt) {
+      s_X[i] = q[i];
+      s_Y[i] = q[n_in + i];
+      s_Z[i] = q[2 * (int64_t)n_in + i];
+      s_vis[i] = 0;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) s_coef[k * P + i] = 0.0f;
+    }
+  }
+  // ---- SetPose: setpose_se3 (pose.cpp:25-76) ----------------------------------------------------------
+  if (tid == 0) {
+    setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p,
+                S.G);
+    S.npix = 0;
+    S.nvis = 0;
+  }
+  __syncthreads();
+  // project_pt_save_rotated (pose.cpp:400-488): camera-frame points frozen for the whole TrackPose
+  for (int i = tid; i < P; i += nt) {
+    const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
+    const float xc = S.G[0] * X + S.G[1] * Y + S.G[2] * Z + S.G[3];
+    const float yc = S.G[4] * X + S.G[5] * Y + S.G[6] * Z + S.G[7];
+    const float zc = S.G[8] * X + S.G[9] * Y + S.G[10] * Z + S.G[11];
+    s_Xc[i] = xc;
+    s_Yc[i] = yc;
+    s_Zc[i] = zc;
+    if (prm.pt2d_out) {   // Get2DPoints(): pt2d[lv_l], odometer.h:30
+      const int l = op.lv_l;
+      prm.pt2d_out[2 * off + i] = (xc / zc) * prm.cam.fx[l] + prm.cam.cx[l];
+      prm.pt2d_out[2 * off + n_in + i] = (yc / zc) * prm.cam.fy[l] + prm.cam.cy[l];
+    }
+  }
+  __syncthreads();
+
+  float* trace = prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
+  int trace_n = 0;   // thread 0 only
+
+  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+    const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
+    const float swo = prm.cam.swo[sl], sho = prm.cam.sho[sl];
+    const int width = prm.cam.width[sl];
+    const float* __restrict__ Iref = fr_ref->I[sl];
+    const float* __restrict__ Dxr = fr_ref->dx[sl];
+    const float* __restrict__ Dyr = fr_ref->dy[sl];
+    const float* __restrict__ Inew = fr_new->I[sl];
+
+    // ---- 4a. per point: reference placement + SD coefficients (odometer.cpp:268-279, 306-326) ---------
+    for (int i = tid; i < P; i += nt) {
+      const float xc = s_Xc[i], yc = s_Yc[i], zc = s_Zc[i];
+      const float mx = (xc / zc) * fx + cx;      // pt2d[sl][i], project_pt at the pose set by SetPose
+      const float my = (yc / zc) * fy + cy;
+      // odometer.cpp:273-275; written so that a NaN centre counts as outside (the reference would index with it)
+      const bool out = !((mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho));
+      if (out) {
+        s_vis[i] = 0;
+      } else {
+        s_vis[i] = 1;
+        const PatchPlace q = patch_place(mx, my, pszd2, width);
+        s_base[i] = q.base;
+        s_w[i] = q.w0; s_w[P + i] = q.w1; s_w[2 * P + i] = q.w2; s_w[3 * P + i] = q.w3;
+        float c[10];
+        sd_coefs(xc, yc, zc, fx, fy, c);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s_coef[k * P + i] = c[k];
+      }
+    }
+    __syncthreads();
+    // ---- 4b. template gather: pat_ref, pat_dx, pat_dy (util_getPatch_grad, utilities.cpp:115-189) -----
+    for (int e = tid; e < E; e += nt) {
+      int i, r, c;
+      elem_split<PSZ>(e, n, psz, i, r, c);
+      if (s_vis[i] & 1) {
+        const int addr = s_base[i] + r * width + c;
+        const float w0 = s_w[i], w1 = s_w[P + i], w2 = s_w[2 * P + i], w3 = s_w[3 * P + i];
+        s_ref[e] = bilin4(Iref, addr, width, w0, w1, w2, w3);
+        s_gx[e] = bilin4(Dxr, addr, width, w0, w1, w2, w3);
+        s_gy[e] = bilin4(Dyr, addr, width, w0, w1, w2, w3);
+      }
+    }
+    if (patchnorm) {
+      __syncthreads();
+      patch_means(s_ref, s_mean, s_vis, 1, P, n, warp, lane, nw);
+      __syncthreads();
+      for (int e = tid; e < E; e += nt) {
+        const int i = e / n;
+        if (s_vis[i] & 1) s_ref[e] = s_ref[e] - s_mean[i];
+      }
+    }
+    // ---- 5+6. steepest-descent values and Hessian (odometer.cpp:302-334, 428-472) ---------------------
+    {
+      float acc[21];
+#pragma unroll
+      for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
+      for (int e = tid; e < E; e += nt) {
+        int i, r, c;
+        elem_split<PSZ>(e, n, psz, i, r, c);
+        float cf[10], sd[6];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cf[k] = s_coef[k * P + i];
+        sd_values(s_gx[e], s_gy[e], cf, sd);
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) { acc[k] = acc[k] + sd[a] * sd[b]; ++k; }
+      }
+#pragma unroll
+      for (int k = 0; k < 21; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) S.part[warp * 21 + k] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < 21) {
+      float s = S.part[tid];
+      for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 21 + tid];
+      S.Hsum[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float H[36];
+      int k = 0;
+      for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) { H[a + 6 * b] = S.Hsum[k]; H[b + 6 * a] = S.Hsum[k]; ++k; }
+      lu6_factor(H, S.lu);                         // factor once; the solves below repeat Eigen's op order
+      S.normdp_init = 1e-10f;                      // odometer.cpp:341-342
+      S.normdp = 1e-10f;
+      S.it = 0;
+      S.cont = (0 < op.maxiter) & ((S.normdp / S.normdp_init) > op.normdp_ratio);
+    }
+    __syncthreads();
+
+    // ---- iterations (odometer.cpp:344-419) -------------------------------------------------------------
+    while (S.cont) {
+      // 7. project_pt with the current pose (pose.cpp:307-397) + new-frame placement
+      for (int i = tid; i < P; i += nt) {
+        const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
+        const float tx = S.G[0] * X + S.G[1] * Y + S.G[2] * Z + S.G[3];
+        const float ty = S.G[4] * X + S.G[5] * Y + S.G[6] * Z + S.G[7];
+        const float tz = S.G[8] * X + S.G[9] * Y + S.G[10] * Z + S.G[11];
+        const float mx = (tx / tz) * fx + cx;
+        const float my = (ty / tz) * fy + cy;
+        const bool out = !((mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho));   // odometer.cpp:369-371
+        if (out) {
+          s_vis[i] &= ~2;
+        } else {
+          s_vis[i] |= 2;
+          const PatchPlace q = patch_place(mx, my, pszd2, width);
+          s_base[i] = q.base;
+          s_w[i] = q.w0; s_w[P + i] = q.w1; s_w[2 * P + i] = q.w2; s_w[3 * P + i] = q.w3;
+          atomicAdd(&S.nvis, 1);
+        }
+      }
+      __syncthreads();
+      // 8. new-frame patch, residual, projection on the SD images
+      float acc[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+      if (patchnorm) {
+        for (int e = tid; e < E; e += nt) {
+          int i, r, c;
+          elem_split<PSZ>(e, n, psz, i, r, c);
+          if (s_vis[i] & 2)
+            s_new[e] = bilin4(Inew, s_base[i] + r * width + c, width, s_w[i], s_w[P + i], s_w[2 * P + i],
+                              s_w[3 * P + i]);
+        }
+        __syncthreads();
+        patch_means(s_new, s_mean, s_vis, 2, P, n, warp, lane, nw);
+        __syncthreads();
+      }
+      for (int e = tid; e < E; e += nt) {
+        int i, r, c;
+        elem_split<PSZ>(e, n, psz, i, r, c);
+        if (s_vis[i] & 2) {
+          float pn;
+          if (patchnorm)
+            pn = s_new[e] - s_mean[i];
+          else
+            pn = bilin4(Inew, s_base[i] + r * width + c, width, s_w[i], s_w[P + i], s_w[2 * P + i], s_w[3 * P + i]);
+          const float pd = s_ref[e] - pn;          // pdiff, odometer.cpp:381
+          float cf[10], sd[6];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) cf[k] = s_coef[k * P + i];
+          sd_values(s_gx[e], s_gy[e], cf, sd);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;   // sd_k_proj then .sum(), :386-404
+        }
+      }
+      // 9a. J^T r: warp shuffle tree, then fixed-order sum over warps
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) S.part[warp * 6 + k] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float sumsd[6], dp[6];
+        for (int k = 0; k < 6; ++k) {
+          float s = S.part[k];
+          for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 6 + k];
+          sumsd[k] = s;
+        }
+        lu6_solve(S.lu, sumsd, dp);                // 9b. odometer.cpp:407
+        for (int k = 0; k < 6; ++k) S.p[k] += dp[k];   // 10. addpose_se3, pose.cpp:116-129
+        se3_exp<float>(S.G, S.p);
+        const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
+                             (fabsf(dp[4]) + fabsf(dp[5]));   // lpNorm<1>, :412
+        if (S.it == 0) S.normdp_init = normdp;
+        S.normdp = normdp;
+        if (trace && trace_n < prm.trace_cap) {
+          float* rec = trace + (int64_t)ICT_TRACE_FLOATS * trace_n++;
+          rec[0] = (float)sl;
+          rec[1] = (float)S.it;
+          for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+          rec[14] = normdp;
+          rec[15] = (float)S.nvis;
+          for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+        }
+        S.npix += (long long)S.nvis * n;
+        S.nvis = 0;
+        S.it += 1;
+        S.cont = (S.it < op.maxiter) & ((S.normdp / S.normdp_init) > op.normdp_ratio);   // :344-346
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
+  }
+
+  if (tid == 0) {
+    getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
+                prm.p_out + 6 * (int64_t)t);
+    if (prm.npixres) prm.npixres[t] = S.npix;
+    if (trace)
+      for (int k = trace_n; k < prm.trace_cap; ++k) {
+        float* rec = trace + (int64_t)ICT_TRACE_FLOATS * k;
+        for (int j = 0; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
+        rec[0] = -1.0f;
+      }
+  }
+}
+
+size_t track_smem_bytes(const ict_optparam& op, int max_pts) {
+  const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
+  const size_t E = (size_t)P * op.novals;
+  const size_t Epad = (E + 3) & ~(size_t)3;
+  const size_t planes = op.dopatchnorm ? 4 : 3;
+  return sizeof(float) * (planes * Epad + (size_t)23 * P) + 16;
+}
+
+template <int PSZ, bool PN>
+static cudaError_t launch_track_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_track<PSZ, PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_track<PSZ, PN><<<prm.T, nt, smem, stream>>>(prm);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream) {
+  if (prm.T <= 0) return cudaSuccess;
+  const size_t smem = track_smem_bytes(prm.op, max_pts);
+  if (smem > (size_t)(227 * 1024 - 8192)) return cudaErrorInvalidConfiguration;
+  const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
+  const long long E = (long long)P * prm.op.novals;
+  const int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
+  const bool pn = prm.op.dopatchnorm != 0;
+  switch (prm.op.psz) {
+    case 8: return pn ? launch_track_t<8, true>(prm, smem, nt, stream) : launch_track_t<8, false>(prm, smem, nt, stream);
+    case 16: return pn ? launch_track_t<16, true>(prm, smem, nt, stream) : launch_track_t<16, false>(prm, smem, nt, stream);
+    case 32: return pn ? launch_track_t<32, true>(prm, smem, nt, stream) : launch_track_t<32, false>(prm, smem, nt, stream);
+    default: return pn ? launch_track_t<0, true>(prm, smem, nt, stream) : launch_track_t<0, false>(prm, smem, nt, stream);
+  }
+}
+
+}  // namespace ict

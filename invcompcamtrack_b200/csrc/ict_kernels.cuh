@@ -1,0 +1,71 @@
+// ict_kernels.cuh — shared declarations between the kernels (ict_kernels.cu) and the C ABI (ict_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ictrack.h"
+
+namespace ict {
+
+// per-level intrinsics, CamClass (camera.cpp:32-43); width = (int)getsw(l) as util_getPatch receives it
+struct CamLevels {
+  float fx[ICT_MAX_LEVELS], fy[ICT_MAX_LEVELS], cx[ICT_MAX_LEVELS], cy[ICT_MAX_LEVELS];
+  float swo[ICT_MAX_LEVELS], sho[ICT_MAX_LEVELS];
+  int width[ICT_MAX_LEVELS];
+};
+
+// device pointers to the padded level planes of one frame
+struct FrameDesc {
+  const float* I[ICT_MAX_LEVELS];
+  const float* dx[ICT_MAX_LEVELS];
+  const float* dy[ICT_MAX_LEVELS];
+};
+
+struct TrackParams {
+  ict_optparam op;
+  CamLevels cam;
+  const FrameDesc* frames;
+  const int* ref_frame;
+  const int* new_frame;
+  int fixed_ref, fixed_new;        // used when ref_frame/new_frame == nullptr (sequence chains)
+  const int64_t* pt_off;           // [T+1]
+  const float* pt3d;               // per track: X block, Y block, Z block (n_t each) at 3*pt_off[t]
+  const double* norm;              // per track: meanshift[3], varval
+  const double* p_in;              // [T*6]
+  double* p_out;                   // [T*6]
+  int* iters;                      // [T*L] or null
+  float* trace;                    // [T*trace_cap*16] or null
+  int trace_cap;
+  long long* npixres;              // [T] or null
+  float* pt2d_out;                 // [2*total] or null: reference 2-D points at lv_l (Get2DPoints)
+  int T;                           // tracks in this launch
+  int t0;                          // first track of this launch (index into the per-track arrays)
+};
+
+// ---- launches (all asynchronous on `stream`) -------------------------------------------------------------------
+// K0: util_constructpyramide for `count` frames.  src is float (src_u8 == nullptr) or uint8.
+cudaError_t launch_pyramid(const float* src_f32, const unsigned char* src_u8, int count, int w, int h, int lv_f,
+                           int pad, float* I, float* dx, float* dy, int64_t plane_floats,
+                           const int64_t* level_off, cudaStream_t stream);
+
+// a5: Set3Dpoints for T tracks (double SoA in, float SoA + normalisation out; pts_mut gets the centred doubles)
+cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, double* pts_mut, float* pt3d,
+                              double* norm, int donorm, int maxpttrack, int max_pts, cudaStream_t stream);
+
+// a6..a18: SetPose + TrackPose, one CTA per track, template + gradients resident in shared memory.
+// Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
+size_t track_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
+// multi-CTA path for one big track (dense alignment: psz=1, millions of points)
+struct BigTrackWork;
+size_t bigtrack_work_bytes(const ict_optparam& op, int64_t npts);
+cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* work, cudaStream_t stream);
+
+// NCC hypothesis scoring, run_track_nposes.cpp:271-355
+cudaError_t launch_ncc(const ict_optparam& op, const CamLevels& cam, const float* img_b, const float* img_r,
+                       const float* img_f, int nback, int nfwd, const int64_t* pt_off, int T, const float* pb,
+                       const float* pr, const float* pf, float* out, cudaStream_t stream);
+
+int64_t launch_count(int reset);
+
+}  // namespace ict

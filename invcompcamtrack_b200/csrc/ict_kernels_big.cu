@@ -1,0 +1,541 @@
+// ict_kernels_big.cu — (1) the multi-CTA form of SetPose + TrackPose for ONE track that is too large for a CTA's
+// shared memory (dense full-frame alignment: psz = 1, one point per pixel, BASELINE config 4), and (2) the NCC
+// hypothesis scoring kernel.
+//
+// Same arithmetic as k_track (ict_kernels.cu); the template (pat_ref, pat_dx, pat_dy) and the per-point state
+// live in a global work buffer that fits the 126 MB L2 for a 1080p frame, reductions are two-stage with a fixed
+// order (thread-strided partials -> warp tree -> CTA partial -> one finishing CTA), and the iteration loop is a
+// fixed sequence of launches whose kernels return immediately once the on-device convergence flag drops, so
+// there is still no host round-trip inside TrackPose.
+#include "ict_kernels.cuh"
+#include "ict_device.cuh"
+
+namespace ict {
+
+int64_t launch_count(int reset);
+void count_launch_external();
+
+struct BigState {
+  float G[12];
+  float p[6];
+  Lu6 lu;
+  float normdp, normdp_init;
+  int cont, it, nvis, trace_n, level_it;
+  long long npix;
+};
+
+struct BigWork {
+  BigState* st;
+  float *ref, *gx, *gy, *pnew;
+  float *coef, *w, *mean, *Xc, *Yc, *Zc;
+  int *base, *vis;
+  float* part;      // [ncta][21]
+  int ncta;
+};
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int big_ncta(int64_t E) {
+  int64_t c = (E + 1023) / 1024;
+  if (c > 148 * 8) c = 148 * 8;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+size_t bigtrack_work_bytes(const ict_optparam& op, int64_t npts) {
+  const int64_t P = npts < op.maxpttrack ? npts : op.maxpttrack;
+  const int64_t E = P * op.novals;
+  size_t b = al(sizeof(BigState));
+  b += 4 * al(sizeof(float) * E);
+  b += al(sizeof(float) * 10 * P) + al(sizeof(float) * 4 * P) + 4 * al(sizeof(float) * P);
+  b += 2 * al(sizeof(int) * P);
+  b += al(sizeof(float) * 21 * big_ncta(E));
+  return b;
+}
+
+static BigWork carve(const ict_optparam& op, int64_t npts, void* work) {
+  const int64_t P = npts < op.maxpttrack ? npts : op.maxpttrack;
+  const int64_t E = P * op.novals;
+  char* c = (char*)work;
+  BigWork w;
+  w.st = (BigState*)c; c += al(sizeof(BigState));
+  w.ref = (float*)c; c += al(sizeof(float) * E);
+  w.gx = (float*)c; c += al(sizeof(float) * E);
+  w.gy = (float*)c; c += al(sizeof(float) * E);
+  w.pnew = (float*)c; c += al(sizeof(float) * E);
+  w.coef = (float*)c; c += al(sizeof(float) * 10 * P);
+  w.w = (float*)c; c += al(sizeof(float) * 4 * P);
+  w.mean = (float*)c; c += al(sizeof(float) * P);
+  w.Xc = (float*)c; c += al(sizeof(float) * P);
+  w.Yc = (float*)c; c += al(sizeof(float) * P);
+  w.Zc = (float*)c; c += al(sizeof(float) * P);
+  w.base = (int*)c; c += al(sizeof(int) * P);
+  w.vis = (int*)c; c += al(sizeof(int) * P);
+  w.part = (float*)c;
+  w.ncta = big_ncta(E);
+  return w;
+}
+
+struct BigArgs {
+  TrackParams prm;
+  BigWork w;
+  int t;
+  int n_in, P;
+  long long E;
+};
+
+// fixed-order CTA reduction of NV per-thread values into part[blockIdx.x*21 + k]
+template <int NV>
+__device__ __forceinline__ void cta_partials(float* acc, float* part) {
+  __shared__ float s_p[8 * 21];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) s_p[warp * 21 + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = s_p[threadIdx.x];
+    for (int wv = 1; wv < nw; ++wv) s = s + s_p[wv * 21 + threadIdx.x];
+    part[blockIdx.x * 21 + threadIdx.x] = s;
+  }
+}
+
+// sum of the CTA partials, fixed order: 256 strided chains -> warp tree -> 8 warps
+template <int NV>
+__device__ __forceinline__ void finish_partials(const float* part, int ncta, float* out /*shared, NV*/) {
+  __shared__ float s_p[8 * 21];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = 0; k < NV; ++k) {
+    float s = 0.0f;
+    for (int c = threadIdx.x; c < ncta; c += blockDim.x) s = s + part[c * 21 + k];
+    s = warp_sum(s);
+    if (lane == 0) s_p[warp * 21 + k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = s_p[threadIdx.x];
+    for (int wv = 1; wv < nw; ++wv) s = s + s_p[wv * 21 + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+__global__ void k_big_init(const BigArgs a) {
+  // ResetOdometer for the element/point state + setpose_se3
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  for (long long e = gid; e < a.E; e += gsz) { a.w.ref[e] = 0.0f; a.w.gx[e] = 0.0f; a.w.gy[e] = 0.0f; }
+  for (long long i = gid; i < a.P; i += gsz) {
+    a.w.vis[i] = 0;
+    for (int k = 0; k < 10; ++k) a.w.coef[(long long)k * a.P + i] = 0.0f;
+  }
+  if (gid == 0) {
+    BigState* S = a.w.st;
+    const ict_optparam& op = a.prm.op;
+    setpose_se3(a.prm.p_in + 6 * (int64_t)a.t, op.donorm != 0, a.prm.norm + 4 * (int64_t)a.t,
+                a.prm.norm[4 * (int64_t)a.t + 3], S->p, S->G);
+    S->npix = 0;
+    S->nvis = 0;
+    S->trace_n = 0;
+    S->cont = 0;
+    S->it = 0;
+  }
+}
+
+__global__ void k_big_project_ref(const BigArgs a) {
+  const BigState* S = a.w.st;
+  const int64_t off = a.prm.pt_off[a.t];
+  const float* q = a.prm.pt3d + 3 * off;
+  const int l = a.prm.op.lv_l;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.P; i += (long long)gridDim.x * blockDim.x) {
+    const float X = q[i], Y = q[a.n_in + i], Z = q[2 * (int64_t)a.n_in + i];
+    const float xc = S->G[0] * X + S->G[1] * Y + S->G[2] * Z + S->G[3];
+    const float yc = S->G[4] * X + S->G[5] * Y + S->G[6] * Z + S->G[7];
+    const float zc = S->G[8] * X + S->G[9] * Y + S->G[10] * Z + S->G[11];
+    a.w.Xc[i] = xc; a.w.Yc[i] = yc; a.w.Zc[i] = zc;
+    if (a.prm.pt2d_out) {
+      a.prm.pt2d_out[2 * off + i] = (xc / zc) * a.prm.cam.fx[l] + a.prm.cam.cx[l];
+      a.prm.pt2d_out[2 * off + a.n_in + i] = (yc / zc) * a.prm.cam.fy[l] + a.prm.cam.cy[l];
+    }
+  }
+}
+
+__global__ void k_big_level_points(const BigArgs a, int sl) {
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.P; i += (long long)gridDim.x * blockDim.x) {
+    const float xc = a.w.Xc[i], yc = a.w.Yc[i], zc = a.w.Zc[i];
+    const float mx = (xc / zc) * fx + cx;
+    const float my = (yc / zc) * fy + cy;
+    const bool out = !((mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho));
+    if (out) {
+      a.w.vis[i] = 0;
+    } else {
+      a.w.vis[i] = 1;
+      const PatchPlace q = patch_place(mx, my, a.prm.op.pszd2, width);
+      a.w.base[i] = q.base;
+      a.w.w[i] = q.w0; a.w.w[a.P + i] = q.w1; a.w.w[2LL * a.P + i] = q.w2; a.w.w[3LL * a.P + i] = q.w3;
+      float c[10];
+      sd_coefs(xc, yc, zc, fx, fy, c);
+      for (int k = 0; k < 10; ++k) a.w.coef[(long long)k * a.P + i] = c[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_big_level_gather(const BigArgs a, int sl) {
+  const int n = a.prm.op.novals, psz = a.prm.op.psz, width = a.prm.cam.width[sl];
+  const int rf = a.prm.fixed_ref;
+  const float* __restrict__ Iref = a.prm.frames[rf].I[sl];
+  const float* __restrict__ Dxr = a.prm.frames[rf].dx[sl];
+  const float* __restrict__ Dyr = a.prm.frames[rf].dy[sl];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    const int rem = (int)(e - i * n), r = rem / psz, c = rem - r * psz;
+    if (a.w.vis[i] & 1) {
+      const int addr = a.w.base[i] + r * width + c;
+      const float w0 = a.w.w[i], w1 = a.w.w[a.P + i], w2 = a.w.w[2LL * a.P + i], w3 = a.w.w[3LL * a.P + i];
+      a.w.ref[e] = bilin4(Iref, addr, width, w0, w1, w2, w3);
+      a.w.gx[e] = bilin4(Dxr, addr, width, w0, w1, w2, w3);
+      a.w.gy[e] = bilin4(Dyr, addr, width, w0, w1, w2, w3);
+    }
+  }
+}
+
+// mean subtraction of each visible patch of buf: one warp per patch, fixed order
+__global__ void k_big_patch_means(const BigArgs a, float* buf, int visbit, int subtract) {
+  const int n = a.prm.op.novals;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = wid; i < a.P; i += nwarps) {
+    if (!(a.w.vis[i] & visbit)) continue;
+    float s = 0.0f;
+    for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
+    s = warp_sum(s);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    const float m = s / n;
+    if (lane == 0) a.w.mean[i] = m;
+    if (subtract)
+      for (int k = lane; k < n; k += 32) buf[i * n + k] = buf[i * n + k] - m;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_big_level_hessian(const BigArgs a) {
+  const int n = a.prm.op.novals;
+  float acc[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    float cf[10], sd[6];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) cf[k] = a.w.coef[(long long)k * a.P + i];
+    sd_values(a.w.gx[e], a.w.gy[e], cf, sd);
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = p; q < 6; ++q) { acc[k] = acc[k] + sd[p] * sd[q]; ++k; }
+  }
+  cta_partials<21>(acc, a.w.part);
+}
+
+__global__ void __launch_bounds__(256) k_big_level_finish(const BigArgs a, int sl) {
+  __shared__ float s_H[21];
+  finish_partials<21>(a.w.part, a.w.ncta, s_H);
+  if (threadIdx.x == 0) {
+    BigState* S = a.w.st;
+    const ict_optparam& op = a.prm.op;
+    float H[36];
+    int k = 0;
+    for (int p = 0; p < 6; ++p)
+      for (int q = p; q < 6; ++q) { H[p + 6 * q] = s_H[k]; H[q + 6 * p] = s_H[k]; ++k; }
+    lu6_factor(H, S->lu);
+    S->normdp_init = 1e-10f;
+    S->normdp = 1e-10f;
+    S->it = 0;
+    S->nvis = 0;
+    S->cont = (0 < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+  }
+  (void)sl;
+}
+
+__global__ void k_big_iter_points(const BigArgs a, int sl) {
+  BigState* S = a.w.st;
+  if (!S->cont) return;
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  const int64_t off = a.prm.pt_off[a.t];
+  const float* q = a.prm.pt3d + 3 * off;
+  int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.P; i += (long long)gridDim.x * blockDim.x) {
+    const float X = q[i], Y = q[a.n_in + i], Z = q[2 * (int64_t)a.n_in + i];
+    const float tx = S->G[0] * X + S->G[1] * Y + S->G[2] * Z + S->G[3];
+    const float ty = S->G[4] * X + S->G[5] * Y + S->G[6] * Z + S->G[7];
+    const float tz = S->G[8] * X + S->G[9] * Y + S->G[10] * Z + S->G[11];
+    const float mx = (tx / tz) * fx + cx;
+    const float my = (ty / tz) * fy + cy;
+    const bool out = !((mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho));
+    if (out) {
+      a.w.vis[i] &= ~2;
+    } else {
+      a.w.vis[i] |= 2;
+      const PatchPlace pp = patch_place(mx, my, a.prm.op.pszd2, width);
+      a.w.base[i] = pp.base;
+      a.w.w[i] = pp.w0; a.w.w[a.P + i] = pp.w1; a.w.w[2LL * a.P + i] = pp.w2; a.w.w[3LL * a.P + i] = pp.w3;
+      ++cnt;
+    }
+  }
+  // integer count: order-independent
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&S->nvis, cnt);
+}
+
+__global__ void __launch_bounds__(256) k_big_iter_sample(const BigArgs a, int sl) {
+  if (!a.w.st->cont) return;
+  const int n = a.prm.op.novals, psz = a.prm.op.psz, width = a.prm.cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    const int rem = (int)(e - i * n), r = rem / psz, c = rem - r * psz;
+    if (a.w.vis[i] & 2)
+      a.w.pnew[e] = bilin4(Inew, a.w.base[i] + r * width + c, width, a.w.w[i], a.w.w[a.P + i], a.w.w[2LL * a.P + i],
+                           a.w.w[3LL * a.P + i]);
+  }
+}
+
+template <bool PN>
+__global__ void __launch_bounds__(256) k_big_iter_elems(const BigArgs a, int sl) {
+  if (!a.w.st->cont) return;
+  const int n = a.prm.op.novals, psz = a.prm.op.psz, width = a.prm.cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  float acc[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    if (a.w.vis[i] & 2) {
+      float pn;
+      if (PN) {
+        pn = a.w.pnew[e];   // mean already subtracted by k_big_patch_means
+      } else {
+        const int rem = (int)(e - i * n), r = rem / psz, c = rem - r * psz;
+        pn = bilin4(Inew, a.w.base[i] + r * width + c, width, a.w.w[i], a.w.w[a.P + i], a.w.w[2LL * a.P + i],
+                    a.w.w[3LL * a.P + i]);
+      }
+      const float pd = a.w.ref[e] - pn;
+      float cf[10], sd[6];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) cf[k] = a.w.coef[(long long)k * a.P + i];
+      sd_values(a.w.gx[e], a.w.gy[e], cf, sd);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;
+    }
+  }
+  cta_partials<6>(acc, a.w.part);
+}
+
+__global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl) {
+  BigState* S = a.w.st;
+  if (!S->cont) return;
+  __shared__ float s_sum[21];
+  finish_partials<6>(a.w.part, a.w.ncta, s_sum);
+  if (threadIdx.x == 0) {
+    const ict_optparam& op = a.prm.op;
+    float sumsd[6], dp[6];
+    for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
+    lu6_solve(S->lu, sumsd, dp);
+    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
+    se3_exp<float>(S->G, S->p);
+    const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
+    if (S->it == 0) S->normdp_init = normdp;
+    S->normdp = normdp;
+    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
+      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
+      rec[0] = (float)sl;
+      rec[1] = (float)S->it;
+      for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+      rec[14] = normdp;
+      rec[15] = (float)S->nvis;
+      for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+    }
+    S->npix += (long long)S->nvis * op.novals;
+    S->nvis = 0;
+    S->it += 1;
+    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+  }
+}
+
+__global__ void k_big_level_end(const BigArgs a, int sl) {
+  const ict_optparam& op = a.prm.op;
+  if (a.prm.iters) a.prm.iters[(int64_t)a.t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = a.w.st->it;
+}
+
+__global__ void k_big_final(const BigArgs a) {
+  BigState* S = a.w.st;
+  const ict_optparam& op = a.prm.op;
+  getpose_se3(S->p, S->G, op.donorm != 0, a.prm.norm + 4 * (int64_t)a.t, a.prm.norm[4 * (int64_t)a.t + 3],
+              a.prm.p_out + 6 * (int64_t)a.t);
+  if (a.prm.npixres) a.prm.npixres[a.t] = S->npix;
+  if (a.prm.trace)
+    for (int k = S->trace_n; k < a.prm.trace_cap; ++k) {
+      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + k) * ICT_TRACE_FLOATS;
+      for (int j = 0; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
+      rec[0] = -1.0f;
+    }
+}
+
+cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* work, cudaStream_t st) {
+  BigArgs a;
+  a.prm = prm;
+  a.w = carve(prm.op, npts, work);
+  a.t = t;
+  a.n_in = (int)npts;
+  a.P = (int)(npts < prm.op.maxpttrack ? npts : prm.op.maxpttrack);
+  a.E = (long long)a.P * prm.op.novals;
+  const ict_optparam& op = prm.op;
+  const int ncta = a.w.ncta;
+  const int pcta = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
+  const bool pn = op.dopatchnorm != 0;
+  int nl = 0;
+  k_big_init<<<ncta, 256, 0, st>>>(a); ++nl;
+  k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
+  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+    k_big_level_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
+    k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
+    if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1); ++nl; }
+    k_big_level_hessian<<<ncta, 256, 0, st>>>(a); ++nl;
+    k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+    for (int it = 0; it < op.maxiter; ++it) {
+      k_big_iter_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
+      if (pn) {
+        k_big_iter_sample<<<ncta, 256, 0, st>>>(a, sl); ++nl;
+        k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.pnew, 2, 1); ++nl;
+        k_big_iter_elems<true><<<ncta, 256, 0, st>>>(a, sl); ++nl;
+      } else {
+        k_big_iter_elems<false><<<ncta, 256, 0, st>>>(a, sl); ++nl;
+      }
+      k_big_iter_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+    }
+    k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
+  }
+  k_big_final<<<1, 1, 0, st>>>(a); ++nl;
+  for (int k = 0; k < nl; ++k) count_launch_external();
+  return cudaGetLastError();
+}
+
+// ==================================================================================================
+// NCC hypothesis scoring, run_track_nposes.cpp:271-355.  One CTA per point; three mean-subtracted psz x psz
+// patches (util_getPatch with dopatchnorm, :281) at level lv_l, each divided by its norm (:317-319),
+// corr = max(0, (max(0,<b,r>)*nback^2 + max(0,<r,f>)*nfwd^2) / (nback^2 + nfwd^2)) (:324-348).
+// Stale patches of invalid points never reach the output in the reference (their weight is 0), so points are
+// independent.
+// ==================================================================================================
+__device__ __forceinline__ float cta_sum(float v, float* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float s = s_red[0];
+  for (int wv = 1; wv < nw; ++wv) s = s + s_red[wv];
+  return s;
+}
+
+__global__ void __launch_bounds__(128) k_ncc(ict_optparam op, CamLevels cam, const float* __restrict__ img_b,
+                                             const float* __restrict__ img_r, const float* __restrict__ img_f,
+                                             int nback, int nfwd, const int64_t* __restrict__ pt_off, int T,
+                                             const float* __restrict__ pb, const float* __restrict__ pr,
+                                             const float* __restrict__ pf, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  __shared__ float s_red[4];
+  __shared__ int s_t;
+  const int n = op.novals, psz = op.psz, l = op.lv_l;
+  const long long g = blockIdx.x;   // global point index
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = T;             // track with pt_off[t] <= g < pt_off[t+1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pt_off[mid] <= g) lo = mid; else hi = mid; }
+    s_t = lo;
+  }
+  __syncthreads();
+  const int t = s_t;
+  const int64_t off = pt_off[t];
+  const int n_t = (int)(pt_off[t + 1] - off);
+  const int i = (int)(g - off);
+  const float swo = cam.swo[l], sho = cam.sho[l];
+  const int width = cam.width[l];
+  const float* imgs[3] = {img_b, img_r, img_f};
+  const float* pts[3] = {pb, pr, pf};
+  bool val[3];
+  float nrm[3];
+  for (int k = 0; k < 3; ++k) {
+    float* buf = sm + k * n;
+    const float mx = pts[k][2 * off + i], my = pts[k][2 * off + n_t + i];
+    val[k] = (mx > 0) & (my > 0) & (mx < swo) & (my < sho);   // strict, :292,299,307
+    float ss = 0.0f;
+    if (val[k]) {
+      const PatchPlace q = patch_place(mx, my, op.pszd2, width);
+      float s = 0.0f;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int r = e / psz, c = e - r * psz;
+        const float v = bilin4(imgs[k], q.base + r * width + c, width, q.w0, q.w1, q.w2, q.w3);
+        buf[e] = v;
+        s = s + v;
+      }
+      const float m = cta_sum(s, s_red) / n;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const float v = buf[e] - m;
+        buf[e] = v;
+        ss = ss + v * v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < n; e += blockDim.x) buf[e] = 0.0f;
+    }
+    nrm[k] = sqrtf(cta_sum(ss, s_red));
+  }
+  float corr = -1.0f;
+  if (val[1]) {
+    float d0 = 0.0f, d1 = 0.0f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const float b = sm[e] / nrm[0], r = sm[n + e] / nrm[1], f = sm[2 * n + e] / nrm[2];
+      d0 = d0 + b * r;
+      d1 = d1 + r * f;
+    }
+    d0 = cta_sum(d0, s_red);
+    d1 = cta_sum(d1, s_red);
+    float corr_br, corr_rf, w0, w1;
+    if (val[0]) { corr_br = 0.0f < d0 ? d0 : 0.0f; w0 = (float)(nback * nback); } else { corr_br = -1.0f; w0 = 0.0f; }
+    if (val[2]) { corr_rf = 0.0f < d1 ? d1 : 0.0f; w1 = (float)(nfwd * nfwd); } else { corr_rf = -1.0f; w1 = 0.0f; }
+    const float v = (corr_br * w0 + corr_rf * w1) / (w0 + w1);
+    corr = 0.0f < v ? v : 0.0f;
+  }
+  if (threadIdx.x == 0) out[g] = corr;
+}
+
+cudaError_t launch_ncc(const ict_optparam& op, const CamLevels& cam, const float* img_b, const float* img_r,
+                       const float* img_f, int nback, int nfwd, const int64_t* pt_off, int T, const float* pb,
+                       const float* pr, const float* pf, float* out, cudaStream_t stream) {
+  // total points = pt_off[T] lives on the device; the caller passes host-known totals through T tracks
+  int64_t total = 0;
+  cudaError_t e = cudaMemcpyAsync(&total, pt_off + T, sizeof(int64_t), cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return e;
+  if (total <= 0) return cudaSuccess;
+  const size_t smem = sizeof(float) * 3 * (size_t)op.novals;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  static bool attr = false;
+  if (!attr) {
+    e = cudaFuncSetAttribute(k_ncc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  k_ncc<<<(unsigned)total, 128, smem, stream>>>(op, cam, img_b, img_r, img_f, nback, nfwd, pt_off, T, pb, pr, pf, out);
+  count_launch_external();
+  return cudaGetLastError();
+}
+
+}  // namespace ict

@@ -43,7 +43,12 @@ def se3_log(G):
 
 
 def _blur(a, sigma):
-    """Separable Gaussian blur with reflect borders (numpy only)."""
+    """Separable Gaussian blur with reflect borders (scipy when present, else numpy)."""
+    try:
+        from scipy.ndimage import gaussian_filter
+        return gaussian_filter(a, sigma, mode="reflect", truncate=3.0)
+    except ImportError:
+        pass
     r = int(3 * sigma + 0.5)
     k = np.exp(-0.5 * (np.arange(-r, r + 1) / sigma) ** 2)
     k /= k.sum()
@@ -58,7 +63,7 @@ def make_texture(seed, h, w):
     """Multi-octave blurred uniform noise, rescaled to [0,255], uint8 — has gradient content at every pyramid level."""
     rng = np.random.default_rng(seed)
     acc = np.zeros((h, w))
-    for sigma, amp in ((2.0, 1.0), (4.0, 1.5), (8.0, 2.0), (16.0, 3.0)):
+    for sigma, amp in ((2.0, 1.0), (4.0, 1.5), (8.0, 2.0), (16.0, 3.0), (32.0, 4.0)):
         n = _blur(rng.random((h, w)) - 0.5, sigma)
         acc += amp * n / n.std()
     acc -= acc.min()
@@ -108,8 +113,10 @@ class Scene:
         return np.clip(np.round(img), 0, 255).astype(np.uint8)
 
     def random_motion(self, seed, scale=1.0):
-        """t ~ U(-0.02,0.02)^3 * depth, w ~ U(-0.01,0.01)^3 rad."""
+        """t ~ U(-0.02,0.02)^3 * depth, w ~ U(-0.01,0.01)^3 rad at 640 px width, scaled by 640/W
+        so that the image flow stays <~ 13 px at level 0 whatever the resolution (a 4-level pyramid recovers it)."""
         rng = np.random.default_rng(2000 + seed)
+        scale = scale * 640.0 / self.w
         t = rng.uniform(-0.02, 0.02, 3) * self.depth * scale
         w = rng.uniform(-0.01, 0.01, 3) * scale
         return np.concatenate([t, w])

@@ -710,6 +710,7 @@ void ict_oracle_trackpose(ict_oracle_odom* o, double* p_out) {
       for (int k = 0; k < 6; ++k) memset(o->sdp[k], 0, sizeof(float) * mn); /* :352-357 */
       project_pt(o, o->pt3d, 0, o->pt2d_new, np, sl);                        /* :360 */
       int nvis = 0;
+      double abssum[6] = {0, 0, 0, 0, 0, 0};
       for (int i = 0; i < np; ++i) { /* :363-396 */
         float mid[2] = {o->pt2d_new[i], o->pt2d_new[i + M]};
         if ((mid[0] < 0) | (mid[1] < 0) | (mid[0] > swo) | (mid[1] > sho)) {
@@ -726,6 +727,11 @@ void ict_oracle_trackpose(ict_oracle_odom* o, double* p_out) {
             const float* s = o->sd[a] + (size_t)i * n;
             float* sp = o->sdp[a] + (size_t)i * n;
             for (int k = 0; k < n; ++k) sp[k] = s[k] * pd[k];
+            if (o->trace) { /* instrumentation only: sum |sd_k * pdiff|, the scale of the summation noise */
+              double as = 0;
+              for (int k = 0; k < n; ++k) as += fabs((double)sp[k]);
+              abssum[a] += as;
+            }
           }
         }
       }
@@ -746,6 +752,8 @@ void ict_oracle_trackpose(ict_oracle_odom* o, double* p_out) {
         for (int a = 0; a < 6; ++a) { r[2 + a] = o->sumsd[a]; r[8 + a] = o->delta_p[a]; }
         r[14] = normdp;
         r[15] = (float)nvis;
+        for (int a = 0; a < 6; ++a) r[16 + a] = (float)abssum[a];
+        r[22] = r[23] = 0.0f;
       }
     }
     o->iters[op->lv_f - sl] = it;

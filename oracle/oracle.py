@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TRACE_FLOATS = 16
+TRACE_FLOATS = 24
 MAX_LEVELS = 8
 
 

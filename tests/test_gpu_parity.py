@@ -1,0 +1,120 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from helpers import make_case, oracle_run, gpu_run, check_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_present(ict):
+    assert ict.device_count() >= 1
+
+
+@pytest.mark.parametrize("w,h,lv_f,pad", [(640, 480, 3, 8), (160, 120, 1, 8), (320, 240, 2, 5), (1920, 1080, 3, 32),
+                                           (64, 48, 3, 1)])
+def test_pyramid_bit_exact(ict, orc, w, h, lv_f, pad):
+    rng = np.random.default_rng(w + lv_f)
+    img = rng.integers(0, 256, (h, w)).astype(np.float32)
+    g = ict.pyramid_build(img, lv_f, pad)
+    o = orc.pyramid_build(img, lv_f, pad)
+    for k in range(3):
+        assert np.array_equal(g[k], o[k])
+
+
+def test_pyramid_u8_upload_equals_float(ict):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (2, 96, 128)).astype(np.uint8)
+    fa = ict.Frames(2, 128, 96, 2, 8); fa.upload(0, img)
+    fb = ict.Frames(2, 128, 96, 2, 8); fb.upload(0, img.astype(np.float32))
+    for f in range(2):
+        for a, b in zip(fa.download(f), fb.download(f)):
+            assert np.array_equal(a, b)
+
+
+CASES = [
+    dict(seed=0),                                            # BASELINE config 1: 640x480, psz 8, 100 points
+    dict(seed=1, donorm=1),
+    dict(seed=2, dopatchnorm=1),
+    dict(seed=3, donorm=1, dopatchnorm=1),
+    dict(seed=4, psz=4, npts=50),
+    dict(seed=5, psz=16, npts=17),
+    dict(seed=6, psz=7, npts=20),                            # odd psz: shifted placement
+    dict(seed=7, psz=32, npts=4, w=1920, h=1080),            # config 3 geometry, one track
+    dict(seed=8, lv_f=2, lv_l=1, maxiter=5, ratio=0.1),
+    dict(seed=9, npts=37, maxpttrack=24),                    # more points than maxpttrack: the rest is ignored
+    dict(seed=10, scale=3.0),                                # large motion: points leave the new frame at some levels
+]
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_track_parity_single(ict, orc, kw):
+    case = make_case(**kw)
+    o = oracle_run(orc, case)
+    g = gpu_run(ict, case)
+    for k in range(3):
+        assert np.array_equal(g["pyr"][0][k], o["pyr"][0][k])
+    assert np.array_equal(g["pt2d"], o["pt2d"])              # reference reprojection: bit-exact
+    assert np.array_equal(g["npixres"], o["npixres"]) or (g["iters"] != o["iters"]).any()
+    res = check_parity(g, o, case, min_same_iters=1.0)
+    print(kw, res, g["iters"][0], np.abs(g["p_out"][0] - case["p_gt"]).max())
+
+
+def test_track_parity_batch(ict, orc):
+    """256 independent tracks of 4 points, 32x32 patches, 1080p (BASELINE config 3 geometry, reduced count)."""
+    case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=256)
+    o = oracle_run(orc, case, trace_cap=48)
+    g = gpu_run(ict, case, trace_cap=48)
+    assert np.array_equal(g["pt2d"], o["pt2d"])
+    res = check_parity(g, o, case)
+    print(res)
+
+
+def test_track_parity_fp64_oracle_brackets(ict, orc):
+    """The GPU's tree sums should sit between the oracle's fp32 packet order and its fp64-accumulate mode."""
+    case = make_case(seed=31, ntracks=8)
+    g = gpu_run(ict, case)
+    o64 = oracle_run(orc, case, sum_mode=2)
+    res = check_parity(g, o64, case, min_same_iters=0.9)
+    print(res)
+
+
+def test_track_pair_entry_point(ict, orc):
+    case = make_case(seed=41, donorm=1)
+    o = oracle_run(orc, case)
+    op = ict.OptParam.from_buffer_copy(bytes(case["op"]))
+    pts = case["pts"].copy()
+    r = ict.track_pair(op, case["sc"].fc, case["sc"].cc, case["sc"].wh, case["A"], case["B"], pts, np.zeros(6),
+                       trace_cap=64)
+    g = dict(p_out=r["p_out"][None], iters=r["iters"][None], trace=r["trace"][None])
+    check_parity(g, o, case, min_same_iters=1.0)
+    # donorm: the caller's points were centred in place, like odometer.cpp:207-212
+    assert abs(pts[:case["npts"]].mean()) < 1e-9 and not np.allclose(pts, case["pts"])
+
+
+def test_sequence_chain(ict, orc):
+    """Forward chain over 6 frames == run_track_nposes.cpp:232-239; GPU chain vs oracle chain, pose by pose."""
+    from invcompcamtrack_b200 import synth
+    from oracle import oracle as O
+    nfr = 6
+    sc, frames, poses = synth.make_sequence(3, nfr, 320, 240)
+    op_o = O.make_optparam(lv_f=2, psz=8, maxpttrack=60)
+    pts = sc.points(77, 60, 8, 2)
+    pyr = [orc.pyramid_build(f.astype(np.float32), 2, 8) for f in frames]
+    p = np.zeros((1, 6))
+    chain = [p.copy()]
+    for k in range(nfr - 1):
+        r = orc.track_batch(op_o, sc.fc, sc.cc, sc.wh, [q[0] for q in pyr], [q[1] for q in pyr], [q[2] for q in pyr],
+                            np.array([0, 60]), pts.copy(), [k], [k + 1], p)
+        p = r["p_out"]
+        chain.append(p.copy())
+    op = ict.OptParam.from_buffer_copy(bytes(op_o))
+    fr = ict.Frames(nfr, 320, 240, 2, 8)
+    fr.upload(0, np.stack(frames))
+    tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_points(np.array([0, 60]), pts.copy())
+    g = tr.track_sequence(fr, 0, nfr - 1, 1, np.zeros(6))
+    for k in range(nfr):
+        assert np.abs(g["poses"][k, 0] - chain[k][0]).max() < 2e-6, k
+    # and the chain actually follows the ground-truth motion
+    assert np.abs(g["poses"][-1, 0] - poses[-1]).max() < 5e-3
