@@ -100,6 +100,13 @@ void ict_tracker_destroy(ict_tracker* tr);
 /* later changes of the caller's optparam (run_track_nposes.cpp:281 flips dopatchnorm mid-run) */
 int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
 
+/* Order of the fp32 reductions (Hessian, J^T r, patch means):
+ *   0 (default) fixed-order parallel tree — deterministic, fastest;
+ *   1 the order of Eigen 3.3's vectorised .sum() with 4-float packets, which is what odometer.cpp:399-404,430-455 run
+ *     (the model oracle/ictrack_oracle.c pins): results are then bit-identical to the oracle, about 3x slower.
+ * The multi-CTA path for oversized tracks always uses 0. */
+int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
+
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:
  *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame
  *   [16..21] sum_k |sd_k * pdiff| — filled by the CPU oracle only (the scale fp32 summation noise is relative to;

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ict_tracker_create": (C.c_void_p, [C.POINTER(OptParam), _f, _f, _i]),
     "ict_tracker_destroy": (None, [C.c_void_p]),
     "ict_tracker_set_optparam": (C.c_int, [C.c_void_p, C.POINTER(OptParam)]),
+    "ict_tracker_set_sum_order": (C.c_int, [C.c_void_p, C.c_int]),
     "ict_tracker_set_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "ict_tracker_set_points_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_void_p]),
@@ -211,6 +212,10 @@ class Tracker:
         _check(lib().ict_tracker_set_optparam(self.h_, C.byref(op)))
         self.op = op
         self.L = op.lv_f - op.lv_l + 1
+
+    def set_sum_order(self, mode):
+        """0: fast fixed-order tree; 1: Eigen packet order (bit-identical to the oracle)."""
+        _check(lib().ict_tracker_set_sum_order(self.h_, int(mode)))
 
     def set_points(self, pt_off, pts, mutate_caller=False):
         """pt_off int64[T+1]; pts float64 [3*total]: per track X block, Y block, Z block."""

@@ -272,6 +272,7 @@ struct ict_tracker {
   int max_pts = 0;
   std::vector<int64_t> h_off;
   bool have_2d = false;
+  int sum_mode = 0;
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
 };
 
@@ -303,6 +304,12 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op) {
   if (op->psz != tr->op.psz || op->lv_f != tr->op.lv_f)
     return fail(ICT_ERR_BAD_ARG, "psz and lv_f are fixed at creation (they size the camera and the pyramids)");
   tr->op = *op;
+  return ICT_OK;
+}
+
+int ict_tracker_set_sum_order(ict_tracker* tr, int mode) {
+  if (!tr || (mode != 0 && mode != 1)) return fail(ICT_ERR_BAD_ARG, "sum order must be 0 (tree) or 1 (reference order)");
+  tr->sum_mode = mode;
   return ICT_OK;
 }
 
@@ -387,8 +394,9 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.pt2d_out = tr->pt2d.as<float>();
   prm.T = tr->T;
   prm.t0 = 0;
-  const size_t smem = track_smem_bytes(tr->op, tr->max_pts);
-  if (smem <= (size_t)(227 * 1024 - 8192)) {
+  prm.sum_mode = tr->sum_mode;
+  const size_t smem = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode);
+  if (smem <= (size_t)ICT_TRACK_SMEM_LIMIT) {
     CU(launch_track(prm, tr->max_pts, st));
   } else {
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
@@ -432,7 +440,7 @@ int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame,
   CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
   CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
   CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
-  const bool big = track_smem_bytes(tr->op, tr->max_pts) > (size_t)(227 * 1024 - 8192);
+  const bool big = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode) > (size_t)ICT_TRACK_SMEM_LIMIT;
   int rc;
   if (big) {
     // multi-CTA path runs one track at a time with fixed frames

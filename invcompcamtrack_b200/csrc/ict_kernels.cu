@@ -267,22 +267,87 @@ __device__ __forceinline__ void elem_split(int e, int n, int psz, int& i, int& r
   }
 }
 
-// mean of each visible patch of `buf` (n values per patch) -> s_mean[i]; one warp per patch, fixed order
+// --------------------------------------------------------------------------------------------------
+// Reference-order reductions (sum_mode 1).  Eigen's vectorised .sum() (the oracle's default model of it:
+// Eigen 3.3 Redux.h, 4-float packets, two accumulators — oracle/ictrack_oracle.c DEF_PACKET_SUM) is eight
+// interleaved SEQUENTIAL fp32 chains: chain c adds v[c], v[8+c], v[16+c], ... in that order.  fp32 addition
+// is not associative, so the only way to reproduce its bits is to run those chains as written: one thread
+// per (quantity, chain), the other threads of the CTA idle.  About 3x slower per iteration than the tree;
+// exists so that parity with the reference can be shown BIT-EXACT and for callers who need
+// reference-identical iteration counts.
+// --------------------------------------------------------------------------------------------------
+// chain c of the two-accumulator body: sum over e = c, c+8, ... < as2 (values beyond `valid` are zeros)
+template <typename F>
+__device__ __forceinline__ float eigen_chain(F v, int c, int as2, int valid) {
+  if (c >= as2) return 0.0f;
+  float s = c < valid ? v(c) : 0.0f;
+  const int lim = as2 < valid ? as2 : valid;
+  for (int e = c + 8; e < lim; e += 8) s = s + v(e);
+  return s;
+}
+// combine the eight chains + the odd packet + the scalar tail exactly like redux_impl::run
+template <typename F>
+__device__ __forceinline__ float eigen_finish(const float* ch, F v, int N, int valid) {
+  const int as1 = (N / 4) * 4, as2 = (N / 8) * 8;
+  auto val = [&](int e) { return e < valid ? v(e) : 0.0f; };
+  float res;
+  if (N == 0) return 0.0f;
+  if (as1) {
+    float p0[4];
+    if (as1 > 4) {
+      for (int j = 0; j < 4; ++j) p0[j] = ch[j] + ch[4 + j];
+      if (as1 > as2)
+        for (int j = 0; j < 4; ++j) p0[j] = p0[j] + val(as2 + j);
+    } else {
+      for (int j = 0; j < 4; ++j) p0[j] = val(j);
+    }
+    res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+    for (int e = as1; e < N; ++e) res = res + val(e);
+  } else {
+    res = val(0);
+    for (int e = 1; e < N; ++e) res = res + val(e);
+  }
+  return res;
+}
+// whole sum by ONE thread (patch means: N = psz*psz)
+template <typename F>
+__device__ __forceinline__ float eigen_sum_serial(F v, int N) {
+  float ch[8];
+  const int as2 = (N / 8) * 8;
+  for (int c = 0; c < 8; ++c) ch[c] = eigen_chain(v, c, as2, N);
+  return eigen_finish(ch, v, N, N);
+}
+
+// mean of each visible patch of `buf` (n values per patch) -> s_mean[i]
+template <bool EX>
 __device__ __forceinline__ void patch_means(const float* buf, float* s_mean, const int* s_vis, int visbit, int P,
-                                            int n, int warp, int lane, int nw) {
-  for (int i = warp; i < P; i += nw) {
-    if (!(s_vis[i] & visbit)) continue;
-    float s = 0.0f;
-    for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
-    s = warp_sum(s);
-    if (lane == 0) s_mean[i] = s / n;   // tmp.sum() / op->novals, utilities.cpp:112,188
+                                            int n, int tid, int nt) {
+  if (EX) {   // reference order, one thread per patch
+    for (int i = tid; i < P; i += nt) {
+      if (!(s_vis[i] & visbit)) continue;
+      const float* b = buf + i * n;
+      s_mean[i] = eigen_sum_serial([&](int e) { return b[e]; }, n) / n;   // tmp.sum() / op->novals, utilities.cpp:112
+    }
+  } else {    // one warp per patch, lane-strided partials + shuffle tree
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int i = warp; i < P; i += nw) {
+      if (!(s_vis[i] & visbit)) continue;
+      float s = 0.0f;
+      for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
+      s = warp_sum(s);
+      if (lane == 0) s_mean[i] = s / n;
+    }
   }
 }
 
-template <int PSZ, bool PN>
+// MODE bit 0: dopatchnorm; bit 1: reference-order (Eigen packet) sums.  Either one needs the fourth plane.
+template <int PSZ, int MODE>
 __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
+  constexpr bool PN = (MODE & 1) != 0;
+  constexpr bool EX = (MODE & 2) != 0;
   extern __shared__ __align__(16) float smem[];
   __shared__ TrackShared S;
+  __shared__ float s_chain[21 * 8];
 
   const int t = blockIdx.x + prm.t0;
   const ict_optparam& op = prm.op;
@@ -294,6 +359,7 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
   const int n_in = (int)(prm.pt_off[t + 1] - off);
   const int P = min(n_in, op.maxpttrack);
   const int E = P * n;
+  const int Nfull = op.maxpttrack * n;               // the reference sums over ALL maxpttrack*novals slots
   const int Epad = (E + 3) & ~3;
   const bool donorm = op.donorm != 0;
   const bool patchnorm = PN && (op.dopatchnorm != 0);
@@ -302,8 +368,8 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
   float* s_ref = smem;
   float* s_gx = s_ref + Epad;
   float* s_gy = s_gx + Epad;
-  float* s_new = s_gy + Epad;                       // only when PN
-  float* s_ptf = PN ? s_new + Epad : s_new;         // per-point floats
+  float* s_new = s_gy + Epad;                       // pat_new (PN) / pdiff (EX); absent when MODE == 0
+  float* s_ptf = MODE ? s_new + Epad : s_new;       // per-point floats
   float* s_X = s_ptf;
   float* s_Y = s_X + P;
   float* s_Z = s_Y + P;
@@ -362,6 +428,20 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
   float* trace = prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
   int trace_n = 0;   // thread 0 only
 
+  // sd_q(e) with the reference's roundings, from shared memory (used by the reference-order chains)
+  auto sd_at = [&](int q, int e) -> float {
+    const int i = PSZ > 0 ? e / (PSZ * PSZ) : e / n;
+    const float gx = s_gx[e], gy = s_gy[e];
+    switch (q) {
+      case 0: return gx * s_coef[0 * P + i];
+      case 1: return gy * s_coef[1 * P + i];
+      case 2: return gx * s_coef[2 * P + i] + gy * s_coef[3 * P + i];
+      case 3: return gx * s_coef[4 * P + i] + gy * s_coef[5 * P + i];
+      case 4: return gx * s_coef[6 * P + i] + gy * s_coef[7 * P + i];
+      default: return gx * s_coef[8 * P + i] + gy * s_coef[9 * P + i];
+    }
+  };
+
   for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
     const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
     const float swo = prm.cam.swo[sl], sho = prm.cam.sho[sl];
@@ -406,7 +486,7 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
     }
     if (patchnorm) {
       __syncthreads();
-      patch_means(s_ref, s_mean, s_vis, 1, P, n, warp, lane, nw);
+      patch_means<EX>(s_ref, s_mean, s_vis, 1, P, n, tid, nt);
       __syncthreads();
       for (int e = tid; e < E; e += nt) {
         const int i = e / n;
@@ -414,7 +494,24 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
       }
     }
     // ---- 5+6. steepest-descent values and Hessian (odometer.cpp:302-334, 428-472) ---------------------
-    {
+    if (EX) {
+      __syncthreads();
+      const int as2 = (Nfull / 8) * 8;
+      if (tid < 21 * 8) {
+        const int q = tid >> 3, c = tid & 7;
+        int a = 0, b = 0, k = 0;                       // q-th pair (a<=b) in the order of ComputeHessian
+        for (int aa = 0; aa < 6; ++aa)
+          for (int bb = aa; bb < 6; ++bb) { if (k == q) { a = aa; b = bb; } ++k; }
+        s_chain[tid] = eigen_chain([&](int e) { return sd_at(a, e) * sd_at(b, e); }, c, as2, E);
+      }
+      __syncthreads();
+      if (tid < 21) {
+        int a = 0, b = 0, k = 0;
+        for (int aa = 0; aa < 6; ++aa)
+          for (int bb = aa; bb < 6; ++bb) { if (k == tid) { a = aa; b = bb; } ++k; }
+        S.Hsum[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return sd_at(a, e) * sd_at(b, e); }, Nfull, E);
+      }
+    } else {
       float acc[21];
 #pragma unroll
       for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
@@ -436,12 +533,12 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
         const float v = warp_sum(acc[k]);
         if (lane == 0) S.part[warp * 21 + k] = v;
       }
-    }
-    __syncthreads();
-    if (tid < 21) {
-      float s = S.part[tid];
-      for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 21 + tid];
-      S.Hsum[tid] = s;
+      __syncthreads();
+      if (tid < 21) {
+        float s = S.part[tid];
+        for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 21 + tid];
+        S.Hsum[tid] = s;
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -480,9 +577,6 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
       }
       __syncthreads();
       // 8. new-frame patch, residual, projection on the SD images
-      float acc[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
       if (patchnorm) {
         for (int e = tid; e < E; e += nt) {
           int i, r, c;
@@ -492,39 +586,70 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
                               s_w[3 * P + i]);
         }
         __syncthreads();
-        patch_means(s_new, s_mean, s_vis, 2, P, n, warp, lane, nw);
+        patch_means<EX>(s_new, s_mean, s_vis, 2, P, n, tid, nt);
         __syncthreads();
       }
-      for (int e = tid; e < E; e += nt) {
-        int i, r, c;
-        elem_split<PSZ>(e, n, psz, i, r, c);
-        if (s_vis[i] & 2) {
-          float pn;
-          if (patchnorm)
-            pn = s_new[e] - s_mean[i];
-          else
-            pn = bilin4(Inew, s_base[i] + r * width + c, width, s_w[i], s_w[P + i], s_w[2 * P + i], s_w[3 * P + i]);
-          const float pd = s_ref[e] - pn;          // pdiff, odometer.cpp:381
-          float cf[10], sd[6];
-#pragma unroll
-          for (int k = 0; k < 10; ++k) cf[k] = s_coef[k * P + i];
-          sd_values(s_gx[e], s_gy[e], cf, sd);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;   // sd_k_proj then .sum(), :386-404
+      if (EX) {
+        // pdiff of every slot (0 where the point is not visible: its sd_proj stays memset to 0, :352-357)
+        for (int e = tid; e < E; e += nt) {
+          int i, r, c;
+          elem_split<PSZ>(e, n, psz, i, r, c);
+          float pd = 0.0f;
+          if (s_vis[i] & 2) {
+            float pn;
+            if (patchnorm)
+              pn = s_new[e] - s_mean[i];
+            else
+              pn = bilin4(Inew, s_base[i] + r * width + c, width, s_w[i], s_w[P + i], s_w[2 * P + i], s_w[3 * P + i]);
+            pd = s_ref[e] - pn;
+          }
+          s_new[e] = pd;
         }
-      }
-      // 9a. J^T r: warp shuffle tree, then fixed-order sum over warps
+        __syncthreads();
+        const int as2 = (Nfull / 8) * 8;
+        if (tid < 6 * 8) {
+          const int q = tid >> 3, c = tid & 7;
+          s_chain[tid] = eigen_chain([&](int e) { return sd_at(q, e) * s_new[e]; }, c, as2, E);
+        }
+        __syncthreads();
+        if (tid < 6)
+          S.part[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return sd_at(tid, e) * s_new[e]; }, Nfull, E);
+      } else {
+        float acc[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) S.part[warp * 6 + k] = v;
+        for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+        for (int e = tid; e < E; e += nt) {
+          int i, r, c;
+          elem_split<PSZ>(e, n, psz, i, r, c);
+          if (s_vis[i] & 2) {
+            float pn;
+            if (patchnorm)
+              pn = s_new[e] - s_mean[i];
+            else
+              pn = bilin4(Inew, s_base[i] + r * width + c, width, s_w[i], s_w[P + i], s_w[2 * P + i], s_w[3 * P + i]);
+            const float pd = s_ref[e] - pn;          // pdiff, odometer.cpp:381
+            float cf[10], sd[6];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) cf[k] = s_coef[k * P + i];
+            sd_values(s_gx[e], s_gy[e], cf, sd);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;   // sd_k_proj then .sum(), :386-404
+          }
+        }
+        // 9a. J^T r: warp shuffle tree, then fixed-order sum over warps
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const float v = warp_sum(acc[k]);
+          if (lane == 0) S.part[warp * 6 + k] = v;
+        }
       }
       __syncthreads();
       if (tid == 0) {
         float sumsd[6], dp[6];
         for (int k = 0; k < 6; ++k) {
           float s = S.part[k];
-          for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 6 + k];
+          if (!EX)
+            for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 6 + k];
           sumsd[k] = s;
         }
         lu6_solve(S.lu, sumsd, dp);                // 9b. odometer.cpp:407
@@ -566,40 +691,52 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
   }
 }
 
-size_t track_smem_bytes(const ict_optparam& op, int max_pts) {
+size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode) {
   const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
   const size_t E = (size_t)P * op.novals;
   const size_t Epad = (E + 3) & ~(size_t)3;
-  const size_t planes = op.dopatchnorm ? 4 : 3;
+  const size_t planes = (op.dopatchnorm || sum_mode) ? 4 : 3;
   return sizeof(float) * (planes * Epad + (size_t)23 * P) + 16;
 }
 
-template <int PSZ, bool PN>
+template <int PSZ, int MODE>
 static cudaError_t launch_track_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_track<PSZ, PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+    cudaError_t e = cudaFuncSetAttribute(k_track<PSZ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ICT_TRACK_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_track<PSZ, PN><<<prm.T, nt, smem, stream>>>(prm);
+  k_track<PSZ, MODE><<<prm.T, nt, smem, stream>>>(prm);
   COUNT_LAUNCH();
   return cudaGetLastError();
 }
 
+template <int PSZ>
+static cudaError_t launch_track_p(const TrackParams& prm, size_t smem, int nt, int mode, cudaStream_t stream) {
+  switch (mode) {
+    case 0: return launch_track_t<PSZ, 0>(prm, smem, nt, stream);
+    case 1: return launch_track_t<PSZ, 1>(prm, smem, nt, stream);
+    case 2: return launch_track_t<PSZ, 2>(prm, smem, nt, stream);
+    default: return launch_track_t<PSZ, 3>(prm, smem, nt, stream);
+  }
+}
+
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
-  const size_t smem = track_smem_bytes(prm.op, max_pts);
-  if (smem > (size_t)(227 * 1024 - 8192)) return cudaErrorInvalidConfiguration;
+  const size_t smem = track_smem_bytes(prm.op, max_pts, prm.sum_mode);
+  if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
   const long long E = (long long)P * prm.op.novals;
   const int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
-  const bool pn = prm.op.dopatchnorm != 0;
+  const int mode = (prm.op.dopatchnorm ? 1 : 0) | (prm.sum_mode ? 2 : 0);
+  const int ntx = (mode & 2) && nt < 192 ? 192 : nt;   // the reference-order Hessian needs 21*8 = 168 threads
   switch (prm.op.psz) {
-    case 8: return pn ? launch_track_t<8, true>(prm, smem, nt, stream) : launch_track_t<8, false>(prm, smem, nt, stream);
-    case 16: return pn ? launch_track_t<16, true>(prm, smem, nt, stream) : launch_track_t<16, false>(prm, smem, nt, stream);
-    case 32: return pn ? launch_track_t<32, true>(prm, smem, nt, stream) : launch_track_t<32, false>(prm, smem, nt, stream);
-    default: return pn ? launch_track_t<0, true>(prm, smem, nt, stream) : launch_track_t<0, false>(prm, smem, nt, stream);
+    case 8: return launch_track_p<8>(prm, smem, ntx, mode, stream);
+    case 16: return launch_track_p<16>(prm, smem, ntx, mode, stream);
+    case 32: return launch_track_p<32>(prm, smem, ntx, mode, stream);
+    default: return launch_track_p<0>(prm, smem, ntx, mode, stream);
   }
 }
 

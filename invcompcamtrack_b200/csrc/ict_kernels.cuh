@@ -39,7 +39,11 @@ struct TrackParams {
   float* pt2d_out;                 // [2*total] or null: reference 2-D points at lv_l (Get2DPoints)
   int T;                           // tracks in this launch
   int t0;                          // first track of this launch (index into the per-track arrays)
+  int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
+                                   //    with the oracle's default model of the reference, ~3x slower)
 };
+
+#define ICT_TRACK_SMEM_LIMIT (227 * 1024 - 8192)
 
 // ---- launches (all asynchronous on `stream`) -------------------------------------------------------------------
 // K0: util_constructpyramide for `count` frames.  src is float (src_u8 == nullptr) or uint8.
@@ -53,7 +57,7 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 
 // a6..a18: SetPose + TrackPose, one CTA per track, template + gradients resident in shared memory.
 // Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
-size_t track_smem_bytes(const ict_optparam& op, int max_pts);
+size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
 // multi-CTA path for one big track (dense alignment: psz=1, millions of points)

@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory.  Run in the BUILD container only (needs /root/reference for
+oracle/_ref and Python cv2):   python tests/golden/make_golden.py
+
+  pyramid_*.npz   util_constructpyramide computed with Python cv2 (an independent implementation of the three OpenCV
+                  calls at utilities.cpp:24,30-31,40-46) on uint8-valued images.
+  track_*.npz     inputs and outputs of the reference's OWN sources (oracle/_ref: utilities/camera/pose/odometer.cpp
+                  compiled against oracle/shim) for Set3Dpoints -> SetPose -> TrackPose, with the per-iteration
+                  (H, J^T r, delta_p) recorded by the shim's fullPivLu().solve() hook.
+  se3.npz         util_SE3_coeff_to_group / util_SE3_group_to_coeff, float and double instantiations (oracle/_ref).
+  getpatch.npz    util_getPatch / util_getPatch_grad at awkward centres (integers >= 256, frac > 1-1e-5, odd psz).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O          # noqa: E402
+from invcompcamtrack_b200 import synth  # noqa: E402
+
+
+def cv2_pyramid(img_u8, lv_f, pad):
+    import cv2
+    prev = img_u8.astype(np.float32)
+    I, dx, dy = [], [], []
+    for l in range(lv_f + 1):
+        cur = prev.copy() if l == 0 else cv2.resize(prev, None, fx=.5, fy=.5, interpolation=cv2.INTER_LINEAR)
+        gx = cv2.Sobel(cur, cv2.CV_32F, 1, 0, ksize=1, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+        gy = cv2.Sobel(cur, cv2.CV_32F, 0, 1, ksize=1, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+        I.append(cv2.copyMakeBorder(cur, pad, pad, pad, pad, cv2.BORDER_REPLICATE).reshape(-1))
+        dx.append(cv2.copyMakeBorder(gx, pad, pad, pad, pad, cv2.BORDER_CONSTANT, value=0).reshape(-1))
+        dy.append(cv2.copyMakeBorder(gy, pad, pad, pad, pad, cv2.BORDER_CONSTANT, value=0).reshape(-1))
+        prev = cur
+    return np.concatenate(I), np.concatenate(dx), np.concatenate(dy)
+
+
+def gen_pyramids():
+    rng = np.random.default_rng(11)
+    cases = {"rand": (rng.integers(0, 256, (64, 96)).astype(np.uint8), 3, 5),
+             "sqrt": (synth.sqrt_image(160, 120), 2, 8),                      # run_io_test.m:8-14
+             "tex": (synth.make_texture(5, 48, 64), 2, 1)}
+    for name, (img, lv_f, pad) in cases.items():
+        I, dx, dy = cv2_pyramid(img, lv_f, pad)
+        np.savez_compressed(os.path.join(HERE, "pyramid_%s.npz" % name), img=img, lv_f=lv_f, pad=pad, I=I, dx=dx, dy=dy)
+
+
+TRACK_CASES = {
+    "base": dict(seed=3, w=160, h=120, psz=8, npts=40, lv_f=2),
+    "donorm": dict(seed=4, w=160, h=120, psz=8, npts=40, lv_f=2, donorm=1),
+    "patchnorm": dict(seed=5, w=160, h=120, psz=8, npts=40, lv_f=2, dopatchnorm=1),
+    "both_odd": dict(seed=6, w=160, h=120, psz=5, npts=30, lv_f=1, donorm=1, dopatchnorm=1),
+    "stale": dict(seed=7, w=160, h=120, psz=8, npts=40, lv_f=2, scale=6.0, edge=True),   # points leave the frames
+    "psz4_cap": dict(seed=8, w=160, h=120, psz=4, npts=50, lv_f=2, maxpttrack=32),
+}
+
+
+def build_track_inputs(kw):
+    kw = dict(kw)
+    edge = kw.pop("edge", False)
+    seed, w, h = kw.pop("seed"), kw.pop("w"), kw.pop("h")
+    scale = kw.pop("scale", 1.0)
+    npts = kw.pop("npts")
+    sc, A, B, p_gt = synth.make_pair(seed, w, h, motion_scale=scale)
+    if edge:   # put the points near the border so that some fall outside at some levels / iterations
+        rng = np.random.default_rng(seed)
+        u = np.concatenate([rng.uniform(0, 6, npts // 2), rng.uniform(w - 8, w - 0.5, npts - npts // 2)])
+        v = rng.uniform(1, h - 1, npts)
+        d = np.stack([(u - sc.cc[0]) / sc.fc[0], (v - sc.cc[1]) / sc.fc[1], np.ones(npts)], 0) * sc.depth
+        pts = np.ascontiguousarray(d.reshape(-1), np.float64)
+    else:
+        pts = sc.points(seed, npts, kw["psz"], kw["lv_f"])
+    op = O.make_optparam(maxpttrack=kw.pop("maxpttrack", npts), **kw)
+    return sc, A, B, p_gt, pts, op
+
+
+def gen_tracks(ref):
+    for name, kw in TRACK_CASES.items():
+        sc, A, B, p_gt, pts, op = build_track_inputs(kw)
+        lv_f, psz = op.lv_f, op.psz
+        tot, off, sw, sh = O.pyramid_layout(A.shape[1], A.shape[0], lv_f, psz)
+        pa = ref.pyramid_build(A.astype(np.float32), lv_f, psz)
+        pb = ref.pyramid_build(B.astype(np.float32), lv_f, psz)
+        od = O.Odometer(ref, op, sc.fc, sc.cc, sc.wh)
+        pmut = pts.copy()
+        od.set3dpoints(pmut)
+        p_in = np.zeros(6) if name != "donorm" else np.array([0.01, -0.02, 0.005, 0.002, -0.001, 0.003])
+        od.setpose(p_in, pa, pb, lv_f, off)
+        pt2d = od.get2dpoints()
+        p_out, solves = ref.track(od, 128)
+        od.close()
+        np.savez_compressed(os.path.join(HERE, "track_%s.npz" % name), A=A, B=B, pts=pts, pts_after=pmut, p_in=p_in,
+                            fc=sc.fc, cc=sc.cc, wh=sc.wh, op=np.frombuffer(bytes(op), np.uint8), p_out=p_out,
+                            solves=solves, pt2d=pt2d, p_gt=p_gt)
+        print(name, "iterations", len(solves), "p_out", p_out)
+
+
+def gen_se3(ref):
+    rng = np.random.default_rng(2)
+    P = np.concatenate([rng.uniform(-1, 1, (24, 6)) * np.array([1, 1, 1, .5, .5, .5]),
+                        rng.uniform(-1, 1, (8, 6)) * np.array([1, 1, 1, 2e-5, 2e-5, 2e-5]),    # Taylor branch
+                        np.zeros((1, 6))])
+    Gf = np.stack([ref.se3_exp(p, np.float32) for p in P])
+    Gd = np.stack([ref.se3_exp(p, np.float64) for p in P])
+    Gf_full, Gd_full = Gf.copy(), Gd.copy()
+    lf = np.stack([ref.se3_log(g, np.float32) for g in Gf_full])
+    ld = np.stack([ref.se3_log(g, np.float64) for g in Gd_full])
+    np.savez_compressed(os.path.join(HERE, "se3.npz"), P=P, Gf=Gf, Gd=Gd, lf=lf, ld=ld)
+
+
+def gen_getpatch(ref):
+    rng = np.random.default_rng(9)
+    w, h, pad = 640, 64, 8
+    img = rng.integers(0, 256, (h, w)).astype(np.float32)
+    out = {}
+    for psz in (8, 5, 1):
+        I, dx, dy = ref.pyramid_build(img, 0, psz)
+        width = w + 2 * psz
+        mids = np.array([[5.0, 7.0], [255.0, 10.0], [256.0, 10.0], [300.0, 20.0], [512.0, 33.0], [100.25, 40.75],
+                         [17.999995, 12.5], [300.99999, 9.000001], [0.0, 0.0], [float(w), float(h)], [639.5, 63.5]],
+                        np.float32)
+        for pn in (0, 1):
+            op = O.make_optparam(lv_f=0, psz=psz, dopatchnorm=pn, maxpttrack=4)
+            pat = np.stack([ref.getpatch(I, m, op, width) for m in mids])
+            g = [ref.getpatch_grad(I, dx, dy, m, op, width) for m in mids]
+            out["p%d_n%d" % (psz, pn)] = pat
+            out["g%d_n%d" % (psz, pn)] = np.stack([np.stack(x) for x in g])
+        out["mids"] = mids
+    np.savez_compressed(os.path.join(HERE, "getpatch.npz"), img=img, **out)
+
+
+if __name__ == "__main__":
+    O.build("ref")
+    ref = O.RefLib()
+    gen_pyramids()
+    gen_tracks(ref)
+    gen_se3(ref)
+    gen_getpatch(ref)
+    print("golden fixtures written to", HERE)

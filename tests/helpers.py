@@ -33,12 +33,13 @@ def oracle_run(orc, case, trace_cap=64, sum_mode=0, nthreads=0, p_in=None):
     return out
 
 
-def gpu_run(ict, case, trace_cap=64, p_in=None):
+def gpu_run(ict, case, trace_cap=64, p_in=None, sum_order=0):
     c = case
     op = ict.OptParam.from_buffer_copy(bytes(c["op"]))
     fr = ict.Frames(2, c["w"], c["h"], c["lv_f"], c["psz"])
     fr.upload(0, np.stack([c["A"], c["B"]]))
     tr = ict.Tracker(op, c["sc"].fc, c["sc"].cc, c["sc"].wh)
+    tr.set_sum_order(sum_order)
     pts = c["pts"].copy()
     tr.set_points(c["pt_off"], pts)
     T = c["T"]
@@ -108,3 +109,13 @@ def check_parity(g, o, case, jtr_tol=1e-5, rot_tol=1e-5, trans_tol=1e-5, min_sam
     assert worst_rot <= rot_tol, res
     assert res["frac_tr_ok"] >= min_trans_ok and res["worst_tr"] <= 10 * trans_tol, res
     return res
+
+
+def assert_bit_identical(g, o):
+    """Reference-order mode (ict_tracker_set_sum_order(1)) against the oracle's default mode: every iteration's
+    J^T r and delta_p, the iteration counts, the pixel-residual counts and the final poses must be EQUAL."""
+    assert np.array_equal(g["iters"], o["iters"])
+    assert np.array_equal(g["npixres"], o["npixres"])
+    gt, ot = g["trace"], o["trace"]
+    assert np.array_equal(gt[..., :16], ot[..., :16]), "per-iteration trace (level, it, J^T r, delta_p, normdp, nvis)"
+    assert np.array_equal(g["p_out"], o["p_out"])
