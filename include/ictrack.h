@@ -87,6 +87,14 @@ int ict_frames_upload_u8(ict_frames* fs, int first, int count, const unsigned ch
 /* Same, the images already being in device memory (float or u8); stream is a cudaStream_t (NULL = default). */
 int ict_frames_build_dev(ict_frames* fs, int first, int count, const float* imgs_dev, void* stream);
 int ict_frames_build_dev_u8(ict_frames* fs, int first, int count, const unsigned char* imgs_dev, void* stream);
+/* Upload PRE-BUILT padded planes (what util_constructpyramide's img_ao_pyr / _dx_pyr / _dy_pyr tables point at) of
+ * one frame: I/dx/dy are plane sets laid out as ict_pyramid_layout describes; dx, dy may be NULL for a frame that is
+ * only ever used as the new image (SetPose takes no gradients for img_new, odometer.cpp:241). */
+int ict_frames_upload_planes(ict_frames* fs, int frame, const float* I, const float* dx, const float* dy);
+/* A store that owns no pixels: its entries alias frames of other stores, so that a (ref, new) pair living in two
+ * stores can be handed to ict_track_batch.  Entry idx := frame src_idx of src (same w, h, lv_f, pad). */
+ict_frames* ict_frames_create_view(int nframes, int w, int h, int lv_f, int pad);
+int ict_frames_alias(ict_frames* view, int idx, const ict_frames* src, int src_idx);
 /* Download one frame's padded planes (any of the outputs may be NULL). */
 int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy);
 

@@ -51,6 +51,9 @@ SIGNATURES = {
     "ict_frames_upload_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ict_frames_build_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ict_frames_build_dev_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ict_frames_upload_planes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ict_frames_create_view": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ict_frames_alias": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "ict_frames_download": (C.c_int, [C.c_void_p, C.c_int, _f, _f, _f]),
     "ict_tracker_create": (C.c_void_p, [C.POINTER(OptParam), _f, _f, _i]),
     "ict_tracker_destroy": (None, [C.c_void_p]),
@@ -147,9 +150,9 @@ def pyramid_build(img, lv_f, pad):
 class Frames:
     """Device-resident pyramids of a set of frames (ict_frames)."""
 
-    def __init__(self, nframes, w, h, lv_f, pad):
+    def __init__(self, nframes, w, h, lv_f, pad, view=False):
         self.nframes, self.w, self.h, self.lv_f, self.pad = nframes, w, h, lv_f, pad
-        self.h_ = lib().ict_frames_create(nframes, w, h, lv_f, pad)
+        self.h_ = (lib().ict_frames_create_view if view else lib().ict_frames_create)(nframes, w, h, lv_f, pad)
         if not self.h_:
             raise IctError("ict_frames_create: " + lib().ict_last_error().decode())
         self.plane_floats = pyramid_layout(w, h, lv_f, pad)[0]
@@ -172,6 +175,16 @@ class Frames:
         else:
             imgs = np.ascontiguousarray(imgs, np.float32)
             _check(lib().ict_frames_upload(self.h_, first, imgs.shape[0], _p(imgs)))
+
+    def upload_planes(self, frame, I, dx=None, dy=None):
+        """Pre-built padded plane sets (e.g. made by another implementation of util_constructpyramide)."""
+        I = np.ascontiguousarray(I, np.float32)
+        dx = None if dx is None else np.ascontiguousarray(dx, np.float32)
+        dy = None if dy is None else np.ascontiguousarray(dy, np.float32)
+        _check(lib().ict_frames_upload_planes(self.h_, frame, _p(I), _p(dx), _p(dy)))
+
+    def alias(self, idx, src, src_idx):
+        _check(lib().ict_frames_alias(self.h_, idx, src.h_, src_idx))
 
     def upload_ptr(self, first, count, host_ptr, u8):
         fn = lib().ict_frames_upload_u8 if u8 else lib().ict_frames_upload

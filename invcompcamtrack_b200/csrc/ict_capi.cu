@@ -154,6 +154,7 @@ struct ict_frames {
   float *I, *dx, *dy;
   FrameDesc* desc;
   DevBuf stage;
+  bool view;
 };
 
 ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
@@ -162,6 +163,7 @@ ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
   fs->nframes = nframes; fs->w = w; fs->h = h; fs->lv_f = lv_f; fs->pad = pad;
   fs->I = fs->dx = fs->dy = nullptr;
   fs->desc = nullptr;
+  fs->view = false;
   fs->plane_floats = ict_pyramid_layout(w, h, lv_f, pad, fs->level_off, fs->sw, fs->sh);
   if (fs->plane_floats < 0 || nframes <= 0) {
     fail(ICT_ERR_BAD_ARG, "ict_frames_create: w,h must be divisible by 2^lv_f, nframes > 0");
@@ -203,6 +205,34 @@ void ict_frames_destroy(ict_frames* fs) {
   delete fs;
 }
 
+ict_frames* ict_frames_create_view(int nframes, int w, int h, int lv_f, int pad) {
+  if (require_device()) return nullptr;
+  ict_frames* fs = new ict_frames();
+  fs->nframes = nframes; fs->w = w; fs->h = h; fs->lv_f = lv_f; fs->pad = pad;
+  fs->I = fs->dx = fs->dy = nullptr;
+  fs->desc = nullptr;
+  fs->view = true;
+  fs->plane_floats = ict_pyramid_layout(w, h, lv_f, pad, fs->level_off, fs->sw, fs->sh);
+  if (fs->plane_floats < 0 || nframes <= 0 || cudaMalloc(&fs->desc, sizeof(FrameDesc) * nframes) != cudaSuccess) {
+    fail(ICT_ERR_BAD_ARG, "ict_frames_create_view: bad geometry or allocation failure");
+    cudaGetLastError();
+    delete fs;
+    return nullptr;
+  }
+  cudaMemset(fs->desc, 0, sizeof(FrameDesc) * nframes);
+  return fs;
+}
+
+int ict_frames_alias(ict_frames* view, int idx, const ict_frames* src, int src_idx) {
+  if (!view || !src || !view->view) return fail(ICT_ERR_BAD_ARG, "ict_frames_alias: first argument must be a view store");
+  if (idx < 0 || idx >= view->nframes || src_idx < 0 || src_idx >= src->nframes)
+    return fail(ICT_ERR_BAD_ARG, "ict_frames_alias: index out of range");
+  if (view->w != src->w || view->h != src->h || view->lv_f != src->lv_f || view->pad != src->pad)
+    return fail(ICT_ERR_BAD_ARG, "ict_frames_alias: geometry mismatch");
+  CU(cudaMemcpyAsync(view->desc + idx, src->desc + src_idx, sizeof(FrameDesc), cudaMemcpyDeviceToDevice, 0));
+  return ICT_OK;
+}
+
 static int frames_range_ok(const ict_frames* fs, int first, int count) {
   if (!fs) return fail(ICT_ERR_BAD_ARG, "null frame store");
   if (first < 0 || count < 0 || first + count > fs->nframes) return fail(ICT_ERR_BAD_ARG, "frame range out of bounds");
@@ -211,6 +241,7 @@ static int frames_range_ok(const ict_frames* fs, int first, int count) {
 
 static int frames_build(ict_frames* fs, int first, int count, const float* f32, const unsigned char* u8,
                         cudaStream_t st) {
+  if (fs->view) return fail(ICT_ERR_BAD_ARG, "a view store owns no pixels: build into the store it aliases");
   CU(launch_pyramid(f32, u8, count, fs->w, fs->h, fs->lv_f, fs->pad, fs->I + (size_t)first * fs->plane_floats,
                     fs->dx + (size_t)first * fs->plane_floats, fs->dy + (size_t)first * fs->plane_floats,
                     fs->plane_floats, fs->level_off, st));
@@ -241,8 +272,20 @@ int ict_frames_upload_u8(ict_frames* fs, int first, int count, const unsigned ch
   return frames_build(fs, first, count, nullptr, fs->stage.as<unsigned char>(), 0);
 }
 
+int ict_frames_upload_planes(ict_frames* fs, int frame, const float* I, const float* dx, const float* dy) {
+  if (frames_range_ok(fs, frame, 1)) return ICT_ERR_BAD_ARG;
+  if (fs->view || !I) return fail(ICT_ERR_BAD_ARG, "ict_frames_upload_planes: needs an owning store and an intensity plane set");
+  const size_t bytes = sizeof(float) * (size_t)fs->plane_floats, o = (size_t)frame * fs->plane_floats;
+  CU(cudaMemcpyAsync(fs->I + o, I, bytes, cudaMemcpyHostToDevice, 0));
+  if (dx) CU(cudaMemcpyAsync(fs->dx + o, dx, bytes, cudaMemcpyHostToDevice, 0));
+  if (dy) CU(cudaMemcpyAsync(fs->dy + o, dy, bytes, cudaMemcpyHostToDevice, 0));
+  CU(cudaStreamSynchronize(0));
+  return ICT_OK;
+}
+
 int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy) {
   if (frames_range_ok(fs, frame, 1)) return ICT_ERR_BAD_ARG;
+  if (fs->view) return fail(ICT_ERR_BAD_ARG, "ict_frames_download: a view store owns no pixels");
   const size_t bytes = sizeof(float) * (size_t)fs->plane_floats, o = (size_t)frame * fs->plane_floats;
   if (out_I) CU(cudaMemcpy(out_I, fs->I + o, bytes, cudaMemcpyDeviceToHost));
   if (out_dx) CU(cudaMemcpy(out_dx, fs->dx + o, bytes, cudaMemcpyDeviceToHost));

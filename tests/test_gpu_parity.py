@@ -2,7 +2,8 @@
 import numpy as np
 import pytest
 
-from helpers import make_case, oracle_run, gpu_run, check_parity, assert_bit_identical
+from helpers import (make_case, oracle_run, gpu_run, check_parity, assert_bit_identical,
+                     check_against_oracle_spread)
 
 pytestmark = pytest.mark.gpu
 
@@ -63,14 +64,16 @@ def test_track_bit_exact_in_reference_order(ict, orc, kw):
 
 @pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
 def test_track_parity_fast_order(ict, orc, kw):
-    """Default (tree) reductions: identical inputs -> J^T r within 1e-5 relative; same trajectory up to fp32
-    summation noise.  A single track cannot carry the 99 % iteration-count gate (see test_track_parity_batch)."""
+    """Default (tree) reductions on identical inputs: first-iteration J^T r within 1e-5 relative of the oracle.  A
+    single track cannot carry statistical gates; the batches below do."""
     case = make_case(**kw)
     o = oracle_run(orc, case)
     g = gpu_run(ict, case)
     assert np.array_equal(g["pt2d"], o["pt2d"])
-    res = check_parity(g, o, case, min_same_iters=0.0, min_trans_ok=0.0)
-    print(kw, res, g["iters"][0], np.abs(g["p_out"][0] - case["p_gt"]).max())
+    res = check_parity(g, o, case, gates=False)
+    assert res["jtr_first"] <= 1e-5, res
+    assert np.abs(g["p_out"][0] - o["p_out"][0]).max() < 5e-3, res      # same basin, same answer up to noise
+    print(kw, res, g["iters"][0])
 
 
 def test_track_bit_exact_batch(ict, orc):
@@ -82,28 +85,27 @@ def test_track_bit_exact_batch(ict, orc):
     assert_bit_identical(g, o)
 
 
-def test_track_parity_batch(ict, orc):
-    """Same batch with the default tree reductions, gated against the north_star tolerances where fp32 summation
-    noise allows it; the oracle's own summation orders (Eigen SSE / AVX / sequential / fp64) flip 2-6 % of the
-    stopping decisions among themselves (tests/test_oracle_golden.py::test_oracle_modes_spread), which bounds what
-    any implementation with a different — here: parallel — order can reach."""
+def test_track_parity_batch_fast_order(ict, orc):
+    """Same batch with the default tree reductions.  4-point tracks are ill-conditioned: the reference itself moves
+    by ~1e-2 relative in translation and flips ~13 % of its stopping decisions when only its summation order changes
+    (oracle modes), so the gate is the oracle's own spread, not an absolute 1e-5."""
     case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=256)
-    o = oracle_run(orc, case, trace_cap=48)
     g = gpu_run(ict, case, trace_cap=48)
-    assert np.array_equal(g["pt2d"], o["pt2d"])
-    res = check_parity(g, o, case, min_same_iters=0.90, min_trans_ok=0.90, jtr_traj_tol=1.0)
-    print(res)
+    m, spread = check_against_oracle_spread(g, case, orc, trace_cap=48)
+    print("gpu", m, "oracle spread", spread)
 
 
 def test_track_parity_c1_many(ict, orc):
-    """BASELINE config 1 geometry (640x480, psz 8, 100 points) x 64 tracks, default order."""
+    """BASELINE config 1 geometry (640x480, psz 8, 100 points) x 64 tracks: bit-exact in reference order; in the
+    default order within the oracle's own spread AND close to the north_star numbers (well-conditioned problem)."""
     case = make_case(seed=31, ntracks=64)
     o = oracle_run(orc, case)
-    g = gpu_run(ict, case)
-    res = check_parity(g, o, case, min_same_iters=0.90, min_trans_ok=0.90, jtr_traj_tol=1.0)
-    print(res)
     gx = gpu_run(ict, case, sum_order=1)
     assert_bit_identical(gx, o)
+    g = gpu_run(ict, case)
+    m, spread = check_against_oracle_spread(g, case, orc)
+    assert m["frac_same"] >= 0.95 and m["worst_rot"] <= 1e-5 and m["median_tr"] <= 1e-5 and m["worst_tr"] <= 1e-4, m
+    print("gpu", m, "oracle spread", spread)
 
 
 def test_track_pair_entry_point(ict, orc):
