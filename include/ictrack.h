@@ -112,6 +112,8 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
  *   0 (default) fixed-order parallel tree — deterministic, fastest;
  *   1 the order of Eigen 3.3's vectorised .sum() with 4-float packets, which is what odometer.cpp:399-404,430-455 run
  *     (the model oracle/ictrack_oracle.c pins): results are then bit-identical to the oracle, about 3x slower.
+ *   2 tree reductions with the general kernel (any psz / dopatchnorm) even where the specialised one applies —
+ *     for tests that compare the two kernels.
  * The multi-CTA path for oversized tracks always uses 0. */
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
 
@@ -151,6 +153,11 @@ int ict_track_batch_dev(ict_tracker* tr, const ict_frames* fs, const int* ref_fr
  * poses_out: double[(nsteps+1)*T*6], entry 0 = p_in. Host buffers. */
 int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nsteps, int step,
                        const double* p_in, double* poses_out, int* iters, int64_t* npixres);
+
+/* SetPose WITHOUT TrackPose (run_track_nposes.cpp:217,240,259 call it only to read Get2DPoints): setpose_se3 + the
+ * reference reprojection at level lv_l for all T tracks.  p_in: host double[T*6]; pt2d_out: host float[2*total],
+ * laid out like ict_tracker_get_2dpoints; may be NULL (then fetch with ict_tracker_get_2dpoints). */
+int ict_tracker_reproject(ict_tracker* tr, const double* p_in, float* pt2d_out);
 
 /* Reference 2-D points of the LAST SetPose at level lv_l (OdometerClass::Get2DPoints, odometer.h:30):
  * out float[2*n_t] per track at 2*pt_off[t]: x block then y block. Host buffer. */

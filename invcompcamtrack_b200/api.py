@@ -68,6 +68,7 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ict_track_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "ict_tracker_reproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ict_tracker_get_2dpoints": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ict_track_pair": (C.c_int, [C.POINTER(OptParam), _f, _f, _i, _f, _f, _d, C.c_int, _d, _d, C.c_void_p,
                                  C.c_void_p, C.c_int]),
@@ -270,6 +271,13 @@ class Tracker:
         _check(lib().ict_track_sequence(self.h_, frames.h_, first, nsteps, step, _p(p_in), _p(poses), _p(iters),
                                         _p(npix)))
         return dict(poses=poses, iters=iters[:nsteps], npixres=npix[:nsteps])
+
+    def reproject(self, p_in):
+        """SetPose without TrackPose: the reference 2-D points at lv_l (x block, y block per track)."""
+        p_in = np.ascontiguousarray(np.broadcast_to(p_in, (self.T, 6)), np.float64)
+        out = np.zeros(2 * self.total, np.float32)
+        _check(lib().ict_tracker_reproject(self.h_, _p(p_in), _p(out)))
+        return out
 
     def get_2dpoints(self):
         out = np.zeros(2 * self.total, np.float32)

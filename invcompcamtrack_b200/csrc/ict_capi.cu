@@ -316,6 +316,7 @@ struct ict_tracker {
   std::vector<int64_t> h_off;
   bool have_2d = false;
   int sum_mode = 0;
+  int force_general = 0;
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
 };
 
@@ -351,8 +352,9 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op) {
 }
 
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode) {
-  if (!tr || (mode != 0 && mode != 1)) return fail(ICT_ERR_BAD_ARG, "sum order must be 0 (tree) or 1 (reference order)");
-  tr->sum_mode = mode;
+  if (!tr || mode < 0 || mode > 2) return fail(ICT_ERR_BAD_ARG, "sum order must be 0 (tree), 1 (reference order) or 2");
+  tr->sum_mode = mode == 1 ? 1 : 0;
+  tr->force_general = mode == 2 ? 1 : 0;
   return ICT_OK;
 }
 
@@ -438,6 +440,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.T = tr->T;
   prm.t0 = 0;
   prm.sum_mode = tr->sum_mode;
+  prm.force_general = tr->force_general;
   const size_t smem = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode);
   if (smem <= (size_t)ICT_TRACK_SMEM_LIMIT) {
     CU(launch_track(prm, tr->max_pts, st));
@@ -536,6 +539,27 @@ int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nst
   if (npixres && nsteps)
     CU(cudaMemcpyAsync(npixres, tr->npix.p, sizeof(long long) * (size_t)T * nsteps, cudaMemcpyDeviceToHost, 0));
   CU(cudaStreamSynchronize(0));
+  return ICT_OK;
+}
+
+int ict_tracker_reproject(ict_tracker* tr, const double* p_in, float* pt2d_out) {
+  if (!tr || !p_in) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (tr->T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
+  CU(tr->p_in.reserve(sizeof(double) * 6 * (size_t)tr->T));
+  CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)tr->T, cudaMemcpyHostToDevice, 0));
+  TrackParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.op = tr->op;
+  prm.cam = tr->cam;
+  prm.pt_off = tr->pt_off.as<int64_t>();
+  prm.pt3d = tr->pt3d.as<float>();
+  prm.norm = tr->norm.as<double>();
+  prm.p_in = tr->p_in.as<double>();
+  prm.pt2d_out = tr->pt2d.as<float>();
+  prm.T = tr->T;
+  CU(launch_reproject(prm, 0));
+  tr->have_2d = true;
+  if (pt2d_out) CU(cudaMemcpy(pt2d_out, tr->pt2d.p, sizeof(float) * 2 * (size_t)tr->total, cudaMemcpyDeviceToHost));
   return ICT_OK;
 }
 

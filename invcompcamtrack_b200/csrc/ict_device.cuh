@@ -13,6 +13,29 @@
 
 namespace ict {
 
+// sin and cos of a double for the tracker's rotation angles.  |x| <= pi/4 (every realistic inter-frame rotation):
+// the fdlibm __kernel_sin / __kernel_cos polynomials with explicit fused multiply-adds (error < 1 ulp of double,
+// so the value narrowed to float equals the correctly rounded one); larger angles take the library routine.  The
+// library's generic path costs several hundred dependent cycles on the one thread the whole CTA waits for.
+__device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
+  if (fabs(x) > 0.78539816339744830962) {
+    sincos(x, sn, cs);
+    return;
+  }
+  const double z = x * x;
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double v = z * x;
+  const double r = __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, S6, S5), S4), S3), S2);
+  *sn = __fma_rn(v, __fma_rn(z, r, S1), x);
+  const double rc = z * __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, C6, C5), C4), C3), C2), C1);
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  *cs = w + (((1.0 - w) - hz) + z * rc);
+}
+
 // ---- util_SE3_coeff_to_group<T>, utilities.h:84-145 ---------------------------------------------------------
 // T=float: the template's unqualified sqrt/sin/cos bind to the double C functions, so those sub-expressions are
 // evaluated in double and narrowed on assignment (see oracle/ictrack_oracle.c, DEF_SE3_EXP).
@@ -27,7 +50,7 @@ __device__ __forceinline__ void se3_exp(T* G, const T* p) {
   T sigsq3 = (sig * sig * sig);
   if ((double)sig > ICT_LIEALG_SIGTHRESH) {
     double sn, cs;
-    sincos((double)sig, &sn, &cs);
+    sincos_small((double)sig, &sn, &cs);
     sa = (T)(sn / (double)sig);
     sb = (T)((1 - cs) / (double)sigsq2);
     sc = (T)(((double)sig - sn) / (double)sigsq3);
@@ -177,6 +200,8 @@ struct Lu6 {
   float lu[36];   // column-major
   int rowtr[6], coltr[6];
   int rank;
+  int pr[6];      // c[k] = b[pr[k]]   == the row transpositions applied in order
+  int qd[6];      // x[qd[k]] = c[k]   == the column transpositions applied last-to-first
 };
 
 static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
@@ -212,6 +237,39 @@ static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
   int rank = 0;
   for (int i = 0; i < nonzero; ++i) rank += (fabsf(LU(i, i)) > premult);
   f.rank = rank;
+  int qc[6];   // x[j] = c[qc[j]]
+  for (int k = 0; k < 6; ++k) { f.pr[k] = k; qc[k] = k; }
+  for (int k = 0; k < 6; ++k)
+    if (f.rowtr[k] != k) { const int t = f.pr[k]; f.pr[k] = f.pr[f.rowtr[k]]; f.pr[f.rowtr[k]] = t; }
+  for (int k = 5; k >= 0; --k)
+    if (f.coltr[k] != k) { const int t = qc[k]; qc[k] = qc[f.coltr[k]]; qc[f.coltr[k]] = t; }
+  for (int j = 0; j < 6; ++j) f.qd[qc[j]] = j;
+#undef LU
+}
+
+// The same solve as lu6_solve for a full-rank factorisation, as straight-line code: identical operations in
+// identical order (column-oriented unit-lower forward substitution, then upper backward substitution), no loops
+// over run-time bounds and no dynamically indexed locals.  f, b and x live in shared memory.
+__device__ __forceinline__ void lu6_solve_full(const Lu6& f, const float* b, float* x) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  float c0 = b[f.pr[0]], c1 = b[f.pr[1]], c2 = b[f.pr[2]], c3 = b[f.pr[3]], c4 = b[f.pr[4]], c5 = b[f.pr[5]];
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  c5 = c5 / LU(5, 5);
+  c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  c4 = c4 / LU(4, 4);
+  c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  c3 = c3 / LU(3, 3);
+  c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  c2 = c2 / LU(2, 2);
+  c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  c1 = c1 / LU(1, 1);
+  c0 = c0 - c1 * LU(0, 1);
+  c0 = c0 / LU(0, 0);
+  x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
 #undef LU
 }
 

@@ -691,6 +691,387 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
   }
 }
 
+// SetPose without TrackPose: pose.cpp:25-76 + project_pt at lv_l (what Get2DPoints returns, odometer.h:30)
+__global__ void __launch_bounds__(128) k_reproject(const TrackParams prm) {
+  __shared__ float s_p[6], s_G[12];
+  const int t = blockIdx.x + prm.t0;
+  const ict_optparam& op = prm.op;
+  const int64_t off = prm.pt_off[t];
+  const int n_in = (int)(prm.pt_off[t + 1] - off);
+  const int P = min(n_in, op.maxpttrack);
+  if (threadIdx.x == 0)
+    setpose_se3(prm.p_in + 6 * (int64_t)t, op.donorm != 0, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], s_p,
+                s_G);
+  __syncthreads();
+  const float* q = prm.pt3d + 3 * off;
+  const int l = op.lv_l;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float X = q[i], Y = q[n_in + i], Z = q[2 * (int64_t)n_in + i];
+    const float xc = s_G[0] * X + s_G[1] * Y + s_G[2] * Z + s_G[3];
+    const float yc = s_G[4] * X + s_G[5] * Y + s_G[6] * Z + s_G[7];
+    const float zc = s_G[8] * X + s_G[9] * Y + s_G[10] * Z + s_G[11];
+    prm.pt2d_out[2 * off + i] = (xc / zc) * prm.cam.fx[l] + prm.cam.cx[l];
+    prm.pt2d_out[2 * off + n_in + i] = (yc / zc) * prm.cam.fy[l] + prm.cam.cy[l];
+  }
+}
+
+cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream) {
+  if (prm.T <= 0) return cudaSuccess;
+  k_reproject<<<prm.T, 128, 0, stream>>>(prm);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+
+// ==================================================================================================
+// K2f — the production form of K2 for the default settings (tree reductions, no patch normalisation,
+// psz in {8,16,32}).  Same arithmetic per pixel and per track as k_track above (which stays as the
+// general path: any psz, dopatchnorm, reference-order sums); what changes is the work decomposition:
+//
+//  * a warp owns a contiguous run of "groups" (32*KT pixels of one point; for psz 32: four consecutive
+//    patch rows, lane = column), so everything that is constant per point — the ten SD coefficients,
+//    the bilinear weights, the patch origin, the visibility — sits in registers and is recomputed only
+//    when the warp moves to another point; no per-point shared-memory traffic in the pixel loop;
+//  * every warp projects the points it works on itself (a dozen flops, all lanes redundantly), so the
+//    iteration needs two CTA barriers instead of three and no per-point staging arrays;
+//  * for psz 32 the row above is carried in registers from one row to the next: 10 gathers per 4
+//    pixels instead of 16 (30 instead of 48 in the template precompute);
+//  * template gather and Hessian accumulation are one pass;
+//  * the cross-warp sums are done by six (21) lanes of warp 0 in parallel before lane 0 solves.
+// Shared memory per CTA: 12 B per template pixel + 64 B per point; four CTAs per SM.
+// ==================================================================================================
+struct FastShared {
+  float G[12];
+  float p[6];
+  float sum[8];
+  float dp[6];
+  float part[8 * 24];
+  float Hsum[21];
+  Lu6 lu;
+  float normdp, normdp_init;
+  int cont, it;
+  long long npix;
+};
+
+template <int PSZ>
+__global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
+  constexpr int N = PSZ * PSZ;                      // pixels per patch
+  constexpr int KT = (N / 32 < 4) ? N / 32 : 4;     // 32-pixel steps per group
+  constexpr int GE = 32 * KT;                       // pixels per group
+  constexpr int GPP = N / GE;                       // groups per point
+  extern __shared__ __align__(16) float smem[];
+  __shared__ FastShared S;
+
+  const int t = blockIdx.x + prm.t0;
+  const ict_optparam& op = prm.op;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int pszd2 = PSZ / 2;
+  const int64_t off = prm.pt_off[t];
+  const int n_in = (int)(prm.pt_off[t + 1] - off);
+  const int P = min(n_in, op.maxpttrack);
+  const int E = P * N;
+  const bool donorm = op.donorm != 0;
+
+  float* s_ref = smem;
+  float* s_gx = s_ref + E;
+  float* s_gy = s_gx + E;
+  float* s_X = s_gy + E;                            // per point: X Y Z (world) Xc Yc Zc (reference camera)
+  float* s_Y = s_X + P;
+  float* s_Z = s_Y + P;
+  float* s_Xc = s_Z + P;
+  float* s_Yc = s_Xc + P;
+  float* s_Zc = s_Yc + P;
+  float* s_coef = s_Zc + P;                         // [P][10], kept across levels for points that go out of view
+
+  const int rf = prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref;
+  const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
+  const FrameDesc* fr_ref = prm.frames + rf;
+  const FrameDesc* fr_new = prm.frames + nf;
+
+  // this warp's run of groups
+  const int G_all = P * GPP;
+  const int gpw = (G_all + nw - 1) / nw;
+  const int g_lo = min(warp * gpw, G_all), g_hi = min(g_lo + gpw, G_all);
+
+  // ---- ResetOdometer + points ----------------------------------------------------------------------
+  for (int e = tid; e < E; e += nt) { s_ref[e] = 0.0f; s_gx[e] = 0.0f; s_gy[e] = 0.0f; }
+  {
+    const float* q = prm.pt3d + 3 * off;
+    for (int i = tid; i < P; i += nt) {
+      s_X[i] = q[i];
+      s_Y[i] = q[n_in + i];
+      s_Z[i] = q[2 * (int64_t)n_in + i];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) s_coef[i * 10 + k] = 0.0f;
+    }
+  }
+  if (tid == 0) {
+    setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p,
+                S.G);
+    S.npix = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += nt) {   // project_pt_save_rotated, pose.cpp:400-488
+    const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
+    const float xc = S.G[0] * X + S.G[1] * Y + S.G[2] * Z + S.G[3];
+    const float yc = S.G[4] * X + S.G[5] * Y + S.G[6] * Z + S.G[7];
+    const float zc = S.G[8] * X + S.G[9] * Y + S.G[10] * Z + S.G[11];
+    s_Xc[i] = xc;
+    s_Yc[i] = yc;
+    s_Zc[i] = zc;
+    if (prm.pt2d_out) {
+      const int l = op.lv_l;
+      prm.pt2d_out[2 * off + i] = (xc / zc) * prm.cam.fx[l] + prm.cam.cx[l];
+      prm.pt2d_out[2 * off + n_in + i] = (yc / zc) * prm.cam.fy[l] + prm.cam.cy[l];
+    }
+  }
+  __syncthreads();
+
+  float* trace = prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
+  int trace_n = 0;
+
+  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+    const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
+    const float swo = prm.cam.swo[sl], sho = prm.cam.sho[sl];
+    const int width = prm.cam.width[sl];
+    const float* __restrict__ Iref = fr_ref->I[sl];
+    const float* __restrict__ Dxr = fr_ref->dx[sl];
+    const float* __restrict__ Dyr = fr_ref->dy[sl];
+    const float* __restrict__ Inew = fr_new->I[sl];
+
+    // ---- 4+5+6: template gather, SD coefficients, Hessian — one pass over this warp's groups ------------
+    {
+      float acc[21];
+#pragma unroll
+      for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
+      int cur = -1;
+      bool vis = false;
+      PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
+      float cf[10];
+      for (int g = g_lo; g < g_hi; ++g) {
+        const int i = g / GPP, gp = g - i * GPP;
+        if (i != cur) {
+          cur = i;
+          const float xc = s_Xc[i], yc = s_Yc[i], zc = s_Zc[i];
+          const float mx = (xc / zc) * fx + cx, my = (yc / zc) * fy + cy;
+          vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);      // odometer.cpp:273-275
+          if (vis) {
+            pl = patch_place(mx, my, pszd2, width);
+            sd_coefs(xc, yc, zc, fx, fy, cf);
+            if (gp == 0 && lane < 10) s_coef[i * 10 + lane] = cf[lane];   // persists for later levels
+          } else {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) cf[k] = s_coef[i * 10 + k];      // stale coefficients
+          }
+        }
+        const int ebase = i * N + gp * GE + lane;
+        if (vis) {
+          if (PSZ == 32) {
+            const int a0 = pl.base + (gp * KT) * width + lane;
+            float ci = __ldg(Iref + a0 - width), di = __ldg(Iref + a0 - width - 1);
+            float cx_ = __ldg(Dxr + a0 - width), dx_ = __ldg(Dxr + a0 - width - 1);
+            float cy_ = __ldg(Dyr + a0 - width), dy_ = __ldg(Dyr + a0 - width - 1);
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              const int a = a0 + j * width;
+              const float ai = __ldg(Iref + a), bi = __ldg(Iref + a - 1);
+              const float ax = __ldg(Dxr + a), bx = __ldg(Dxr + a - 1);
+              const float ay = __ldg(Dyr + a), by = __ldg(Dyr + a - 1);
+              s_ref[ebase + 32 * j] = ((pl.w0 * ai + pl.w1 * bi) + pl.w2 * ci) + pl.w3 * di;
+              s_gx[ebase + 32 * j] = ((pl.w0 * ax + pl.w1 * bx) + pl.w2 * cx_) + pl.w3 * dx_;
+              s_gy[ebase + 32 * j] = ((pl.w0 * ay + pl.w1 * by) + pl.w2 * cy_) + pl.w3 * dy_;
+              ci = ai; di = bi; cx_ = ax; dx_ = bx; cy_ = ay; dy_ = by;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              const int q = gp * GE + 32 * j + lane, r = q / PSZ, c = q - r * PSZ;
+              const int a = pl.base + r * width + c;
+              s_ref[ebase + 32 * j] = bilin4(Iref, a, width, pl.w0, pl.w1, pl.w2, pl.w3);
+              s_gx[ebase + 32 * j] = bilin4(Dxr, a, width, pl.w0, pl.w1, pl.w2, pl.w3);
+              s_gy[ebase + 32 * j] = bilin4(Dyr, a, width, pl.w0, pl.w1, pl.w2, pl.w3);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          float sd[6];
+          sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);   // own writes: no barrier needed
+          int k = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) { acc[k] = acc[k] + sd[a] * sd[b]; ++k; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 21; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) S.part[warp * 24 + k] = v;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane < 21) {
+        float s = S.part[lane];
+        for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 24 + lane];
+        S.Hsum[lane] = s;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        float H[36];
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+          for (int b = a; b < 6; ++b) { H[a + 6 * b] = S.Hsum[k]; H[b + 6 * a] = S.Hsum[k]; ++k; }
+        lu6_factor(H, S.lu);
+        S.normdp_init = 1e-10f;
+        S.normdp = 1e-10f;
+        S.it = 0;
+        S.cont = (0 < op.maxiter) & ((S.normdp / S.normdp_init) > op.normdp_ratio);
+      }
+    }
+    __syncthreads();
+
+    // ---- iterations --------------------------------------------------------------------------------
+    while (S.cont) {
+      float Gm[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) Gm[k] = S.G[k];
+      float acc[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+      int nvis = 0;   // points this warp is the first to touch and that are visible in the new frame
+      int cur = -1;
+      bool vis = false;
+      PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
+      float cf[10];
+      for (int g = g_lo; g < g_hi; ++g) {
+        const int i = g / GPP, gp = g - i * GPP;
+        if (i != cur) {
+          cur = i;
+          const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];       // project_pt, pose.cpp:307-397
+          const float tx = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
+          const float ty = Gm[4] * X + Gm[5] * Y + Gm[6] * Z + Gm[7];
+          const float tz = Gm[8] * X + Gm[9] * Y + Gm[10] * Z + Gm[11];
+          const float mx = (tx / tz) * fx + cx, my = (ty / tz) * fy + cy;
+          vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);   // odometer.cpp:369-371
+          if (vis) {
+            pl = patch_place(mx, my, pszd2, width);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) cf[k] = s_coef[i * 10 + k];
+            nvis += (gp == 0);
+          }
+        }
+        if (!vis) continue;
+        const int ebase = i * N + gp * GE + lane;
+        if (PSZ == 32) {
+          const int a0 = pl.base + (gp * KT) * width + lane;
+          float c_ = __ldg(Inew + a0 - width), d_ = __ldg(Inew + a0 - width - 1);
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const float a_ = __ldg(Inew + a0 + j * width), b_ = __ldg(Inew + a0 + j * width - 1);
+            const float pn = ((pl.w0 * a_ + pl.w1 * b_) + pl.w2 * c_) + pl.w3 * d_;
+            c_ = a_; d_ = b_;
+            const float pd = s_ref[ebase + 32 * j] - pn;
+            float sd[6];
+            sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const int q = gp * GE + 32 * j + lane, r = q / PSZ, c = q - r * PSZ;
+            const float pn = bilin4(Inew, pl.base + r * width + c, width, pl.w0, pl.w1, pl.w2, pl.w3);
+            const float pd = s_ref[ebase + 32 * j] - pn;
+            float sd[6];
+            sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) S.part[warp * 24 + k] = v;
+      }
+      if (lane == 0) S.part[warp * 24 + 6] = (float)nvis;
+      __syncthreads();
+      if (warp == 0) {
+        if (lane < 7) {   // 9a. cross-warp sums, fixed order, seven lanes in parallel
+          float s = S.part[lane];
+          for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 24 + lane];
+          S.sum[lane] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (S.lu.rank == 6)
+            lu6_solve_full(S.lu, S.sum, S.dp);     // 9b. odometer.cpp:407
+          else
+            lu6_solve(S.lu, S.sum, S.dp);
+          float dp[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; S.p[k] += dp[k]; }   // 10. addpose_se3
+          se3_exp<float>(S.G, S.p);
+          const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
+                               (fabsf(dp[4]) + fabsf(dp[5]));
+          if (S.it == 0) S.normdp_init = normdp;
+          S.normdp = normdp;
+          const int nv = (int)S.sum[6];
+          if (trace && trace_n < prm.trace_cap) {
+            float* rec = trace + (int64_t)ICT_TRACE_FLOATS * trace_n++;
+            rec[0] = (float)sl;
+            rec[1] = (float)S.it;
+            for (int k = 0; k < 6; ++k) { rec[2 + k] = S.sum[k]; rec[8 + k] = dp[k]; }
+            rec[14] = normdp;
+            rec[15] = (float)nv;
+            for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+          }
+          S.npix += (long long)nv * N;
+          S.it += 1;
+          S.cont = (S.it < op.maxiter) & ((S.normdp / S.normdp_init) > op.normdp_ratio);
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
+  }
+
+  if (tid == 0) {
+    getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
+                prm.p_out + 6 * (int64_t)t);
+    if (prm.npixres) prm.npixres[t] = S.npix;
+    if (trace)
+      for (int k = trace_n; k < prm.trace_cap; ++k) {
+        float* rec = trace + (int64_t)ICT_TRACE_FLOATS * k;
+        for (int j = 0; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
+        rec[0] = -1.0f;
+      }
+  }
+}
+
+static size_t fast_smem_bytes(const ict_optparam& op, int max_pts) {
+  const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
+  return sizeof(float) * (3 * P * op.novals + 16 * P);
+}
+
+template <int PSZ>
+static cudaError_t launch_track_fast_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_track_fast<PSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ICT_TRACK_SMEM_LIMIT);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_track_fast<PSZ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_track_fast<PSZ><<<prm.T, nt, smem, stream>>>(prm);
+  COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode) {
   const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
   const size_t E = (size_t)P * op.novals;
@@ -731,6 +1112,14 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
   const long long E = (long long)P * prm.op.novals;
   const int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
   const int mode = (prm.op.dopatchnorm ? 1 : 0) | (prm.sum_mode ? 2 : 0);
+  if (mode == 0 && !prm.force_general && (prm.op.psz == 8 || prm.op.psz == 16 || prm.op.psz == 32)) {
+    const size_t fsm = fast_smem_bytes(prm.op, max_pts);
+    switch (prm.op.psz) {
+      case 8: return launch_track_fast_t<8>(prm, fsm, nt, stream);
+      case 16: return launch_track_fast_t<16>(prm, fsm, nt, stream);
+      default: return launch_track_fast_t<32>(prm, fsm, nt, stream);
+    }
+  }
   const int ntx = (mode & 2) && nt < 192 ? 192 : nt;   // the reference-order Hessian needs 21*8 = 168 threads
   switch (prm.op.psz) {
     case 8: return launch_track_p<8>(prm, smem, ntx, mode, stream);

@@ -39,6 +39,7 @@ struct TrackParams {
   float* pt2d_out;                 // [2*total] or null: reference 2-D points at lv_l (Get2DPoints)
   int T;                           // tracks in this launch
   int t0;                          // first track of this launch (index into the per-track arrays)
+  int force_general;               // 1: always use the general kernel k_track (tests compare the two)
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
                                    //    with the oracle's default model of the reference, ~3x slower)
 };
@@ -59,6 +60,9 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 // Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
+// SetPose only: setpose_se3 + reprojection at lv_l into prm.pt2d_out (one CTA per track)
+cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream);
 
 // multi-CTA path for one big track (dense alignment: psz=1, millions of points)
 struct BigTrackWork;

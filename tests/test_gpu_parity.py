@@ -108,6 +108,26 @@ def test_track_parity_c1_many(ict, orc):
     print("gpu", m, "oracle spread", spread)
 
 
+@pytest.mark.parametrize("kw", [dict(seed=51, ntracks=8), dict(seed=52, psz=16, npts=9, ntracks=5),
+                                dict(seed=53, psz=32, npts=4, w=1920, h=1080, ntracks=64),
+                                dict(seed=54, psz=32, npts=7, w=1920, h=1080, ntracks=3), dict(seed=55, scale=3.0, ntracks=4),
+                                dict(seed=56, npts=37, maxpttrack=24, ntracks=3), dict(seed=57, donorm=1, ntracks=4)])
+def test_fast_kernel_equals_general_kernel_up_to_sum_order(ict, orc, kw):
+    """k_track_fast (production) and k_track (general) run the same per-pixel arithmetic; only the order of the tree
+    sums differs.  First-iteration J^T r must agree to fp32 summation noise, both with the oracle and each other,
+    and both must count the same pixel-residuals on the first iterations."""
+    case = make_case(**kw)
+    o = oracle_run(orc, case)
+    gf = gpu_run(ict, case, sum_order=0)
+    gg = gpu_run(ict, case, sum_order=2)
+    assert np.array_equal(gf["pt2d"], gg["pt2d"]) and np.array_equal(gf["pt2d"], o["pt2d"])
+    for g in (gf, gg):
+        res = check_parity(g, o, case, gates=False)
+        assert res["jtr_first"] <= 1e-5, res
+        assert np.array_equal(g["trace"][:, 0, 15], o["trace"][:, 0, 15])      # visible points, first iteration
+    assert np.abs(gf["p_out"] - gg["p_out"]).max() < 5e-3
+
+
 def test_track_pair_entry_point(ict, orc):
     case = make_case(seed=41, donorm=1)
     o = oracle_run(orc, case)
@@ -142,8 +162,16 @@ def test_sequence_chain(ict, orc):
     fr.upload(0, np.stack(frames))
     tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
     tr.set_points(np.array([0, 60]), pts.copy())
+    tr.set_sum_order(1)                                   # reference order: the whole chain is bit-identical
     g = tr.track_sequence(fr, 0, nfr - 1, 1, np.zeros(6))
     for k in range(nfr):
-        assert np.abs(g["poses"][k, 0] - chain[k][0]).max() < 2e-6, k
+        assert np.array_equal(g["poses"][k, 0], chain[k][0]), k
+    tr.set_sum_order(0)                                   # default order: same chain up to fp32 summation noise
+    g = tr.track_sequence(fr, 0, nfr - 1, 1, np.zeros(6))
+    for k in range(nfr):
+        assert np.abs(g["poses"][k, 0] - chain[k][0]).max() < 1e-4, k
     # and the chain actually follows the ground-truth motion
     assert np.abs(g["poses"][-1, 0] - poses[-1]).max() < 2e-2
+    # backward chain from the last frame returns to the start (run_track_nposes.cpp:251-258)
+    b = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, g["poses"][-1, 0])
+    assert np.abs(b["poses"][-1, 0]).max() < 2e-2
