@@ -114,7 +114,8 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
  *     (the model oracle/ictrack_oracle.c pins): results are then bit-identical to the oracle, about 3x slower.
  *   2 tree reductions with the general kernel (any psz / dopatchnorm) even where the specialised one applies —
  *     for tests that compare the two kernels.
- * The multi-CTA path for oversized tracks always uses 0. */
+ * The multi-CTA path for oversized tracks honours 0 and 1 for the Hessian and J^T r (its patch means, only used with
+ * dopatchnorm, are always warp trees). */
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
 
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:

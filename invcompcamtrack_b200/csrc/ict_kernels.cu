@@ -276,48 +276,6 @@ __device__ __forceinline__ void elem_split(int e, int n, int psz, int& i, int& r
 // exists so that parity with the reference can be shown BIT-EXACT and for callers who need
 // reference-identical iteration counts.
 // --------------------------------------------------------------------------------------------------
-// chain c of the two-accumulator body: sum over e = c, c+8, ... < as2 (values beyond `valid` are zeros)
-template <typename F>
-__device__ __forceinline__ float eigen_chain(F v, int c, int as2, int valid) {
-  if (c >= as2) return 0.0f;
-  float s = c < valid ? v(c) : 0.0f;
-  const int lim = as2 < valid ? as2 : valid;
-  for (int e = c + 8; e < lim; e += 8) s = s + v(e);
-  return s;
-}
-// combine the eight chains + the odd packet + the scalar tail exactly like redux_impl::run
-template <typename F>
-__device__ __forceinline__ float eigen_finish(const float* ch, F v, int N, int valid) {
-  const int as1 = (N / 4) * 4, as2 = (N / 8) * 8;
-  auto val = [&](int e) { return e < valid ? v(e) : 0.0f; };
-  float res;
-  if (N == 0) return 0.0f;
-  if (as1) {
-    float p0[4];
-    if (as1 > 4) {
-      for (int j = 0; j < 4; ++j) p0[j] = ch[j] + ch[4 + j];
-      if (as1 > as2)
-        for (int j = 0; j < 4; ++j) p0[j] = p0[j] + val(as2 + j);
-    } else {
-      for (int j = 0; j < 4; ++j) p0[j] = val(j);
-    }
-    res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
-    for (int e = as1; e < N; ++e) res = res + val(e);
-  } else {
-    res = val(0);
-    for (int e = 1; e < N; ++e) res = res + val(e);
-  }
-  return res;
-}
-// whole sum by ONE thread (patch means: N = psz*psz)
-template <typename F>
-__device__ __forceinline__ float eigen_sum_serial(F v, int N) {
-  float ch[8];
-  const int as2 = (N / 8) * 8;
-  for (int c = 0; c < 8; ++c) ch[c] = eigen_chain(v, c, as2, N);
-  return eigen_finish(ch, v, N, N);
-}
-
 // mean of each visible patch of `buf` (n values per patch) -> s_mean[i]
 template <bool EX>
 __device__ __forceinline__ void patch_means(const float* buf, float* s_mean, const int* s_vis, int visbit, int P,

@@ -2,7 +2,8 @@
 // shared memory (dense full-frame alignment: psz = 1, one point per pixel, BASELINE config 4), and (2) the NCC
 // hypothesis scoring kernel.
 //
-// Same arithmetic as k_track (ict_kernels.cu); the template (pat_ref, pat_dx, pat_dy) and the per-point state
+// Same arithmetic as k_track (ict_kernels.cu), including the optional reference-order sums (sum_mode 1: Hessian and
+// J^T r by one CTA running Eigen's eight sequential chains); the template (pat_ref, pat_dx, pat_dy) and the per-point state
 // live in a global work buffer that fits the 126 MB L2 for a 1080p frame, reductions are two-stage with a fixed
 // order (thread-strided partials -> warp tree -> CTA partial -> one finishing CTA), and the iteration loop is a
 // fixed sequence of launches whose kernels return immediately once the on-device convergence flag drops, so
@@ -338,11 +339,16 @@ __global__ void __launch_bounds__(256) k_big_iter_elems(const BigArgs a, int sl)
   cta_partials<6>(acc, a.w.part);
 }
 
-__global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl) {
+__global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl, int ncta) {
   BigState* S = a.w.st;
   if (!S->cont) return;
   __shared__ float s_sum[21];
-  finish_partials<6>(a.w.part, a.w.ncta, s_sum);
+  if (ncta == 1) {   // reference-order sums were completed by k_big_iter_sums_exact: take them as they are
+    if (threadIdx.x < 6) s_sum[threadIdx.x] = a.w.part[threadIdx.x];
+    __syncthreads();
+  } else {
+    finish_partials<6>(a.w.part, ncta, s_sum);
+  }
   if (threadIdx.x == 0) {
     const ict_optparam& op = a.prm.op;
     float sumsd[6], dp[6];
@@ -367,6 +373,94 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
     S->it += 1;
     S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
   }
+}
+
+// ---- reference-order (sum_mode 1) variants: one CTA, one thread per (quantity, chain) ---------------------------
+__device__ __forceinline__ float big_sd_at(const BigArgs& a, int q, long long e) {
+  const long long i = e / a.prm.op.novals;
+  const float gx = a.w.gx[e], gy = a.w.gy[e];
+  const float* cf = a.w.coef;
+  switch (q) {
+    case 0: return gx * cf[0 * (long long)a.P + i];
+    case 1: return gy * cf[1 * (long long)a.P + i];
+    case 2: return gx * cf[2 * (long long)a.P + i] + gy * cf[3 * (long long)a.P + i];
+    case 3: return gx * cf[4 * (long long)a.P + i] + gy * cf[5 * (long long)a.P + i];
+    case 4: return gx * cf[6 * (long long)a.P + i] + gy * cf[7 * (long long)a.P + i];
+    default: return gx * cf[8 * (long long)a.P + i] + gy * cf[9 * (long long)a.P + i];
+  }
+}
+
+__global__ void __launch_bounds__(192) k_big_level_hessian_exact(const BigArgs a) {
+  __shared__ float s_chain[21 * 8];
+  __shared__ float s_H[21];
+  const int tid = threadIdx.x;
+  const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E, as2 = (Nfull / 8) * 8;
+  auto pair_of = [](int q, int& x, int& y) {
+    int k = 0;
+    for (int aa = 0; aa < 6; ++aa)
+      for (int bb = aa; bb < 6; ++bb) { if (k == q) { x = aa; y = bb; } ++k; }
+  };
+  if (tid < 21 * 8) {
+    int x = 0, y = 0;
+    pair_of(tid >> 3, x, y);
+    s_chain[tid] = eigen_chain([&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, tid & 7, as2, E);
+  }
+  __syncthreads();
+  if (tid < 21) {
+    int x = 0, y = 0;
+    pair_of(tid, x, y);
+    s_H[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, Nfull, E);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    BigState* S = a.w.st;
+    const ict_optparam& op = a.prm.op;
+    float H[36];
+    int k = 0;
+    for (int p = 0; p < 6; ++p)
+      for (int q = p; q < 6; ++q) { H[p + 6 * q] = s_H[k]; H[q + 6 * p] = s_H[k]; ++k; }
+    lu6_factor(H, S->lu);
+    S->normdp_init = 1e-10f;
+    S->normdp = 1e-10f;
+    S->it = 0;
+    S->nvis = 0;
+    S->cont = (0 < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+  }
+}
+
+// pdiff of every slot into w.pnew (0 where the point is not visible in the new frame)
+template <bool PN>
+__global__ void __launch_bounds__(256) k_big_iter_pdiff(const BigArgs a, int sl) {
+  if (!a.w.st->cont) return;
+  const int n = a.prm.op.novals, psz = a.prm.op.psz, width = a.prm.cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n;
+    float pd = 0.0f;
+    if (a.w.vis[i] & 2) {
+      float pn;
+      if (PN) {
+        pn = a.w.pnew[e];
+      } else {
+        const int rem = (int)(e - i * n), r = rem / psz, c = rem - r * psz;
+        pn = bilin4(Inew, a.w.base[i] + r * width + c, width, a.w.w[i], a.w.w[a.P + i], a.w.w[2LL * a.P + i],
+                    a.w.w[3LL * a.P + i]);
+      }
+      pd = a.w.ref[e] - pn;
+    }
+    a.w.pnew[e] = pd;
+  }
+}
+
+__global__ void __launch_bounds__(64) k_big_iter_sums_exact(const BigArgs a) {
+  if (!a.w.st->cont) return;
+  __shared__ float s_chain[6 * 8];
+  const int tid = threadIdx.x;
+  const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E, as2 = (Nfull / 8) * 8;
+  if (tid < 48) s_chain[tid] = eigen_chain([&](int e) { return big_sd_at(a, tid >> 3, e) * a.w.pnew[e]; }, tid & 7, as2, E);
+  __syncthreads();
+  if (tid < 6)   // the finishing kernel reads partials as part[cta*21 + k] with ncta CTAs: publish as CTA 0 of 1
+    a.w.part[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, tid, e) * a.w.pnew[e]; }, Nfull, E);
 }
 
 __global__ void k_big_level_end(const BigArgs a, int sl) {
@@ -400,6 +494,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const int ncta = a.w.ncta;
   const int pcta = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
   const bool pn = op.dopatchnorm != 0;
+  const bool ex = prm.sum_mode != 0;   // reference-order sums (patch means stay warp trees here)
   int nl = 0;
   k_big_init<<<ncta, 256, 0, st>>>(a); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
@@ -407,18 +502,27 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
     k_big_level_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
     k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1); ++nl; }
-    k_big_level_hessian<<<ncta, 256, 0, st>>>(a); ++nl;
-    k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+    if (ex) {
+      k_big_level_hessian_exact<<<1, 192, 0, st>>>(a); ++nl;
+    } else {
+      k_big_level_hessian<<<ncta, 256, 0, st>>>(a); ++nl;
+      k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+    }
     for (int it = 0; it < op.maxiter; ++it) {
       k_big_iter_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
       if (pn) {
         k_big_iter_sample<<<ncta, 256, 0, st>>>(a, sl); ++nl;
         k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.pnew, 2, 1); ++nl;
-        k_big_iter_elems<true><<<ncta, 256, 0, st>>>(a, sl); ++nl;
-      } else {
-        k_big_iter_elems<false><<<ncta, 256, 0, st>>>(a, sl); ++nl;
       }
-      k_big_iter_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+      if (ex) {
+        if (pn) k_big_iter_pdiff<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_pdiff<false><<<ncta, 256, 0, st>>>(a, sl);
+        ++nl;
+        k_big_iter_sums_exact<<<1, 64, 0, st>>>(a); ++nl;
+      } else {
+        if (pn) k_big_iter_elems<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_elems<false><<<ncta, 256, 0, st>>>(a, sl);
+        ++nl;
+      }
+      k_big_iter_finish<<<1, 256, 0, st>>>(a, sl, ex ? 1 : ncta); ++nl;
     }
     k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
   }

@@ -84,10 +84,12 @@ def _bilinear(tex, x, y):
 
 
 class Scene:
-    """Fronto-parallel textured plane Z=depth in the world frame (= camera frame of pose 0)."""
+    """Textured plane n . X = depth, n = (tilt_x, tilt_y, 1), in the world frame (= camera frame of pose 0); the
+    default tilt (0, 0) is the fronto-parallel plane Z = depth, a non-zero tilt gives every pixel its own depth."""
 
-    def __init__(self, seed, w, h, depth=5.0, margin=None):
+    def __init__(self, seed, w, h, depth=5.0, margin=None, tilt=(0.0, 0.0)):
         self.w, self.h, self.depth = w, h, depth
+        self.n = np.array([tilt[0], tilt[1], 1.0])
         self.margin = margin if margin is not None else max(32, w // 8)
         self.tex = make_texture(1000 + seed, h + 2 * self.margin, w + 2 * self.margin)
         self.fc = np.array([w, w], np.float32)                       # fx = fy = W
@@ -103,7 +105,7 @@ class Scene:
         d = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u)], 0).reshape(3, -1)
         Rtd = R.T @ d
         Rtt = R.T @ t
-        lam = (self.depth + Rtt[2]) / Rtd[2]
+        lam = (self.depth + self.n @ Rtt) / (self.n @ Rtd)
         Xw = Rtd * lam - Rtt[:, None]
         xa = Xw[0] / Xw[2] * fx + cx + self.margin
         ya = Xw[1] / Xw[2] * fy + cy + self.margin
@@ -129,21 +131,35 @@ class Scene:
         u = rng.uniform(m, self.w - m, n)
         v = rng.uniform(m, self.h - m, n)
         fx, fy, cx, cy = float(self.fc[0]), float(self.fc[1]), float(self.cc[0]), float(self.cc[1])
+        return self.backproject(u, v, p_ref)
+
+    def backproject(self, u, v, p_ref=None):
+        """World points on the plane seen at pixels (u, v) of the camera at pose p_ref; SoA float64 [3n]."""
+        fx, fy, cx, cy = float(self.fc[0]), float(self.fc[1]), float(self.cc[0]), float(self.cc[1])
+        u = np.asarray(u, np.float64).reshape(-1)
+        v = np.asarray(v, np.float64).reshape(-1)
         d = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u)], 0)
         if p_ref is None or np.allclose(p_ref, 0):
-            Xw = d * self.depth
+            Xw = d * (self.depth / (self.n @ d))
         else:
             G = se3_exp(p_ref)
             R, t = G[:3, :3], G[:3, 3]
             Rtd, Rtt = R.T @ d, R.T @ t
-            lam = (self.depth + Rtt[2]) / Rtd[2]
+            lam = (self.depth + self.n @ Rtt) / (self.n @ Rtd)
             Xw = Rtd * lam - Rtt[:, None]
         return np.ascontiguousarray(Xw.reshape(-1), np.float64)
 
+    def dense_points(self, border, step=1):
+        """One point per pixel of the reference frame (pose 0) inside a border: the dense-alignment template with
+        per-pixel depth (BASELINE config 4: psz = 1).  Returns SoA float64 [3n]."""
+        u, v = np.meshgrid(np.arange(border, self.w - border, step, dtype=np.float64),
+                           np.arange(border, self.h - border, step, dtype=np.float64))
+        return self.backproject(u, v)
 
-def make_pair(seed, w=640, h=480, depth=5.0, motion_scale=1.0):
+
+def make_pair(seed, w=640, h=480, depth=5.0, motion_scale=1.0, tilt=(0.0, 0.0)):
     """(scene, frame A at pose 0, frame B at pose p_gt, p_gt).  The tracker starts from p=0 and must recover p_gt."""
-    sc = Scene(seed, w, h, depth)
+    sc = Scene(seed, w, h, depth, tilt=tilt)
     p_gt = sc.random_motion(seed, motion_scale)
     return sc, sc.render(np.zeros(6)), sc.render(p_gt), p_gt
 

@@ -6,9 +6,17 @@ from oracle import oracle as O
 
 
 def make_case(seed, w=640, h=480, psz=8, npts=100, lv_f=3, lv_l=0, maxiter=10, ratio=0.01, donorm=0, dopatchnorm=0,
-              scale=1.0, ntracks=1, maxpttrack=None):
-    """One frame pair + ntracks independent point sets.  Returns a dict with everything both sides need."""
-    sc, A, B, p_gt = synth.make_pair(seed, w, h, motion_scale=scale)
+              scale=1.0, ntracks=1, maxpttrack=None, tilt=(0.0, 0.0), dense_border=None):
+    """One frame pair + ntracks independent point sets.  Returns a dict with everything both sides need.
+    dense_border: one track with one point per pixel inside that border (dense alignment, psz = 1)."""
+    sc, A, B, p_gt = synth.make_pair(seed, w, h, motion_scale=scale, tilt=tilt)
+    if dense_border is not None:
+        pts = sc.dense_points(dense_border)
+        npts, ntracks = pts.size // 3, 1
+        op = O.make_optparam(lv_f=lv_f, lv_l=lv_l, psz=psz, maxiter=maxiter, normdp_ratio=ratio, donorm=donorm,
+                             dopatchnorm=dopatchnorm, maxpttrack=npts)
+        return dict(sc=sc, A=A, B=B, p_gt=p_gt, op=op, pts=pts, pt_off=np.array([0, npts], np.int64), w=w, h=h,
+                    psz=psz, lv_f=lv_f, T=1, npts=npts)
     op = O.make_optparam(lv_f=lv_f, lv_l=lv_l, psz=psz, maxiter=maxiter, normdp_ratio=ratio, donorm=donorm,
                          dopatchnorm=dopatchnorm, maxpttrack=maxpttrack or npts)
     pts = np.concatenate([sc.points(seed * 131 + t, npts, psz, lv_f) for t in range(ntracks)])

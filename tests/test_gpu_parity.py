@@ -175,3 +175,53 @@ def test_sequence_chain(ict, orc):
     # backward chain from the last frame returns to the start (run_track_nposes.cpp:251-258)
     b = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, g["poses"][-1, 0])
     assert np.abs(b["poses"][-1, 0]).max() < 2e-2
+
+
+@pytest.mark.parametrize("kw", [dict(seed=61, w=320, h=240, lv_f=2, psz=1, dense_border=8, tilt=(0.15, -0.1)),
+                                dict(seed=62, w=320, h=240, lv_f=2, psz=1, dense_border=6, tilt=(0.1, 0.2), donorm=1),
+                                dict(seed=63, w=160, h=120, lv_f=1, psz=8, npts=900)])
+def test_dense_alignment_multi_cta_path(ict, orc, kw):
+    """BASELINE config 4 geometry (reduced): one track with one point per pixel and per-pixel depth, psz = 1 — too
+    large for a CTA, so the multi-CTA path runs.  Bit-exact against the oracle in reference order; within fp32
+    summation noise in the default order; recovers the ground-truth motion."""
+    case = make_case(**kw)
+    assert case["npts"] * case["op"].novals * 12 > 227 * 1024
+    o = oracle_run(orc, case, trace_cap=48)
+    gx = gpu_run(ict, case, trace_cap=48, sum_order=1)
+    assert np.array_equal(gx["pt2d"], o["pt2d"])
+    assert_bit_identical(gx, o)
+    g = gpu_run(ict, case, trace_cap=48)
+    res = check_parity(g, o, case, gates=False)
+    assert res["jtr_first"] <= 1e-5, res
+    assert np.abs(g["p_out"][0] - o["p_out"][0]).max() < 1e-3, res
+    if kw["psz"] == 1:   # psz = 1 samples both images one pixel up-left (SURVEY §9.3): biased but it follows the motion
+        assert np.abs(g["p_out"][0] - case["p_gt"]).max() < 0.25 * np.abs(case["p_gt"]).max()
+    print(res, g["iters"], o["iters"])
+
+
+def test_ncc_scoring(ict, orc):
+    """run_track_nposes.cpp:271-355 on the GPU vs the oracle: per-point weighted NCC of back / reference / forward
+    patches, including points outside the frames (corr = -1 when the reference point is out, weight 0 otherwise)."""
+    from invcompcamtrack_b200 import synth
+    from oracle import oracle as O
+    sc, frames, poses = synth.make_sequence(5, 3, 320, 240)
+    op_o = O.make_optparam(lv_f=2, psz=8, maxpttrack=64)
+    rng = np.random.default_rng(3)
+    n = 64
+    def pts2d(jit):
+        x = rng.uniform(-5, 325, n).astype(np.float32); y = rng.uniform(-5, 245, n).astype(np.float32)
+        return np.concatenate([x, y])
+    pr = pts2d(0)
+    pb = (pr + rng.normal(0, 0.7, 2 * n)).astype(np.float32)
+    pf = (pr + rng.normal(0, 0.7, 2 * n)).astype(np.float32)
+    pyr = [orc.pyramid_build(f.astype(np.float32), 2, 8) for f in frames]
+    ref = orc.ncc_score(op_o, sc.fc, sc.cc, sc.wh, pyr[0][0], pyr[1][0], pyr[2][0], 1, 1, pb, pr, pf)
+    op = ict.OptParam.from_buffer_copy(bytes(op_o))
+    fr = ict.Frames(3, 320, 240, 2, 8)
+    fr.upload(0, np.stack(frames))
+    tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_points(np.array([0, n]), sc.points(1, n, 8, 2))
+    got = tr.ncc_score(fr, 0, 1, 2, 1, 1, pb, pr, pf)
+    assert (ref == -1).any() and (ref > 0.5).any()
+    assert np.array_equal(got == -1, ref == -1)
+    assert np.abs(got - ref).max() < 2e-5
