@@ -9,6 +9,8 @@ oracle/_ref and Python cv2):   python tests/golden/make_golden.py
                   (H, J^T r, delta_p) recorded by the shim's fullPivLu().solve() hook.
   se3.npz         util_SE3_coeff_to_group / util_SE3_group_to_coeff, float and double instantiations (oracle/_ref).
   getpatch.npz    util_getPatch / util_getPatch_grad at awkward centres (integers >= 256, frac > 1-1e-5, odd psz).
+  drivers.npz     inputs and outputs of the reference's own main()s: run_track_nposes.cpp (text in/out, forward and
+                  backward chains, NCC) and run_io_reprojection_test.cpp (binary in/out), compiled into oracle/_ref.
 """
 import os
 import sys
@@ -131,6 +133,67 @@ def gen_getpatch(ref):
     np.savez_compressed(os.path.join(HERE, "getpatch.npz"), img=img, **out)
 
 
+def write_pgm(path, img):
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
+
+
+def nposes_inputs():
+    """A small run_track_nposes problem: 4 frames (1 back, 2 forward), 60 correspondences, 3 pose samples."""
+    sc, frames, poses = synth.make_sequence(9, 4, 160, 120, motion_scale=0.3)
+    nb, nf = 1, 2
+    pts = sc.points(5, 60, 8, 2, p_ref=poses[nb]).reshape(3, -1).T          # world points seen in the reference frame
+    rng = np.random.default_rng(4)
+    samples = []
+    for s in range(3):
+        p = poses[nb] + rng.normal(0, 1, 6) * np.array([2e-3, 2e-3, 2e-3, 3e-4, 3e-4, 3e-4]) * (s > 0)
+        ids = np.sort(rng.choice(60, size=(24, 32, 40)[s], replace=False)) + 1
+        samples.append((p, ids))
+    lines = ["2 0 8 10 0.01 0 0 40 0", "%g %g %g %g %d %d" % (sc.fc[0], sc.fc[1], sc.cc[0], sc.cc[1], 160, 120),
+             "%d %d" % (nb, nf)]
+    lines += ["@DIR@/f%d.pgm" % k for k in range(4)]
+    lines.append("%d" % len(pts))
+    lines += ["0 0 %.17g %.17g %.17g" % tuple(x) for x in pts]
+    lines.append("%d" % len(samples))
+    for p, ids in samples:
+        lines.append(" ".join("%.17g" % v for v in p) + " %d " % len(ids) + " ".join(str(i) for i in ids))
+    return frames, "\n".join(lines) + "\n", sc
+
+
+def gen_drivers():
+    """Golden outputs of the reference's own DRIVERS (oracle/_ref/run_track_nposes, run_io_reprojection_test: the
+    reference mains compiled against the stand-in headers; the stand-in imread reads binary PGM)."""
+    import struct
+    import subprocess
+    import tempfile
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    frames, template, sc = nposes_inputs()
+    with tempfile.TemporaryDirectory() as d:
+        for k, f in enumerate(frames):
+            write_pgm(os.path.join(d, "f%d.pgm" % k), f)
+        open(os.path.join(d, "in.txt"), "w").write(template.replace("@DIR@", d))
+        subprocess.run([os.path.join(ref_dir, "run_track_nposes"), os.path.join(d, "in.txt"), os.path.join(d, "out.txt")],
+                       check=True)
+        out = open(os.path.join(d, "out.txt")).read()
+        # single pair: frames 1 -> 2, 50 points, binary input of run_io_reprojection_test.cpp:54-79
+        pts = sc.points(6, 50, 8, 2).reshape(3, -1)
+        blob = struct.pack("<6d2f2f2IQ", *([0.0] * 6), float(sc.fc[0]), float(sc.fc[1]), float(sc.cc[0]), float(sc.cc[1]),
+                           160, 120, 50)
+        blob += pts.astype("<f8").tobytes() + np.zeros(100, "<f4").tobytes()
+        open(os.path.join(d, "pair.bin"), "wb").write(blob)
+        args = "2 0 8 10 0.01 0 0 50 0".split()
+        subprocess.run([os.path.join(ref_dir, "run_io_reprojection_test"), os.path.join(d, "f0.pgm"),
+                        os.path.join(d, "f1.pgm"), os.path.join(d, "pair.bin"), os.path.join(d, "pair.out")] + args,
+                       check=True)
+        pair_out = np.frombuffer(open(os.path.join(d, "pair.out"), "rb").read(), "<f8")
+    np.savez_compressed(os.path.join(HERE, "drivers.npz"), frames=np.stack(frames), nposes_input=template,
+                        nposes_output=out, pair_input=np.frombuffer(blob, np.uint8), pair_args=" ".join(args),
+                        pair_output=pair_out)
+    print("run_track_nposes golden:\n" + out[:400])
+    print("run_io_reprojection_test golden:", pair_out)
+
+
 if __name__ == "__main__":
     O.build("ref")
     ref = O.RefLib()
@@ -138,4 +201,5 @@ if __name__ == "__main__":
     gen_tracks(ref)
     gen_se3(ref)
     gen_getpatch(ref)
+    gen_drivers()
     print("golden fixtures written to", HERE)
