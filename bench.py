@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--psz", type=int, default=32)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--cpu-seqs", type=int, default=env_int("ICT_BENCH_CPU_SEQS", 2), help="sequences in the CPU sample")
+    ap.add_argument("--cpu-seqs", type=int, default=env_int("ICT_BENCH_CPU_SEQS", 8), help="sequences in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--textures", type=int, default=4, help="distinct textures shared by the sequences (setup time)")
@@ -311,9 +311,10 @@ def main():
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        # the one collective of the path: gather the per-track poses (6 f64) and iteration counts
-        gathered = [torch.empty_like(d_pout) for _ in range(world)]
-        dist.all_gather(gathered, d_pout)
+        # the one collective of the path: gather the per-track poses (6 f64) and iteration counts, once
+        from invcompcamtrack_b200.shard import gather_results
+        all_poses, all_iters = gather_results(d_pout, d_iters)
+        assert all_poses.shape[0] == NT * world
         ms_total, ms_kernel, ms_e2e_all = mx[0].item(), mx[1].item(), mx[2].item()
         npix_job = sm[3].item()
     else:
