@@ -121,7 +121,8 @@ int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:
  *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame
  *   [16..21] sum_k |sd_k * pdiff| — filled by the CPU oracle only (the scale fp32 summation noise is relative to;
- *            used to normalise the J^T r parity gate), 0 from the GPU   [22..23] reserved
+ *            used to normalise the J^T r parity gate), 0 from the GPU
+ *   [22] SM cycles of the serial solve/update section, [23] of warp 0's pixel section (production kernel only, else 0)
  * Track t owns records [t*trace_cap, (t+1)*trace_cap); unused records have level = -1. */
 #define ICT_TRACE_FLOATS 24
 

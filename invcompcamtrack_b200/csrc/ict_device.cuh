@@ -88,6 +88,63 @@ __device__ __forceinline__ void se3_exp(T* G, const T* p) {
   G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
 }
 
+// Production-kernel form of the float instantiation above.  sin(s)/s, (1-cos s)/s^2 and (s-sin s)/s^3 are even power
+// series in s; with z = s*s formed exactly in double from the float s they are evaluated by Horner in double (ten
+// terms: truncation < 1e-18 for s <= pi/4), so the three values narrowed to float equal the reference's
+// double-evaluated quotients except when one of those lies within ~1e-16 relative of a float rounding boundary.
+// No double division, no double sqrt (sqrtf of a float equals the double sqrt narrowed), three independent
+// fused-multiply-add chains: this runs on the single thread the whole CTA waits for.
+__device__ __forceinline__ void se3_exp_f32_series(float* G, const float* p) {
+  const float ra1 = p[3] * p[3];
+  const float ra2 = p[4] * p[4];
+  const float ra3 = p[5] * p[5];
+  const float sig = sqrtf(ra1 + ra2 + ra3);
+  if (!((double)sig > ICT_LIEALG_SIGTHRESH) || sig > 0.78539816f) {
+    se3_exp<float>(G, p);   // Taylor branch of the reference, or a rotation too large for the short series
+    return;
+  }
+  const double z = (double)sig * (double)sig;
+  // 1/(2k+1)!, 1/(2k+2)!, 1/(2k+3)! with alternating signs, k = 9 .. 0
+  double a = -8.2206352466243297e-18, b = -4.1103176233121648e-19, c = -1.9572941063391263e-20;
+  a = __fma_rn(a, z, 2.8114572543455206e-15);  b = __fma_rn(b, z, 1.5619206968586225e-16); c = __fma_rn(c, z, 8.2206352466243297e-18);
+  a = __fma_rn(a, z, -7.6471637318198164e-13); b = __fma_rn(b, z, -4.7794773323873853e-14);  c = __fma_rn(c, z, -2.8114572543455206e-15);
+  a = __fma_rn(a, z, 1.6059043836821613e-10);  b = __fma_rn(b, z, 1.1470745597729725e-11); c = __fma_rn(c, z, 7.6471637318198164e-13);
+  a = __fma_rn(a, z, -2.5052108385441720e-08); b = __fma_rn(b, z, -2.0876756987868100e-09);  c = __fma_rn(c, z, -1.6059043836821613e-10);
+  a = __fma_rn(a, z, 2.7557319223985893e-06);  b = __fma_rn(b, z, 2.7557319223985888e-07); c = __fma_rn(c, z, 2.5052108385441720e-08);
+  a = __fma_rn(a, z, -1.9841269841269841e-04); b = __fma_rn(b, z, -2.4801587301587302e-05);  c = __fma_rn(c, z, -2.7557319223985893e-06);
+  a = __fma_rn(a, z, 8.3333333333333332e-03);  b = __fma_rn(b, z, 1.3888888888888889e-03); c = __fma_rn(c, z, 1.9841269841269841e-04);
+  a = __fma_rn(a, z, -1.6666666666666666e-01); b = __fma_rn(b, z, -4.1666666666666664e-02);  c = __fma_rn(c, z, -8.3333333333333332e-03);
+  a = __fma_rn(a, z, 1.0);                     b = __fma_rn(b, z, 0.5);                     c = __fma_rn(c, z, 1.6666666666666666e-01);
+  const float sa = (float)a, sb = (float)b, sc = (float)c;
+  float tmp1 = ra2 * sb;
+  float tmp2 = ra3 * sb;
+  float tmp3 = ra1 * sb;
+  float tmp4 = p[3] * p[4] * sb;
+  float tmp5 = p[5] * sa;
+  float tmp6 = p[3] * p[5] * sb;
+  float tmp7 = p[4] * sa;
+  float tmp8 = p[3] * sa;
+  float tmp9 = p[4] * p[5] * sb;
+  G[0] = 1 - tmp1 - tmp2;
+  G[1] = tmp4 - tmp5;
+  G[2] = tmp7 + tmp6;
+  G[4] = tmp5 + tmp4;
+  G[5] = 1 - tmp3 - tmp2;
+  G[6] = tmp9 - tmp8;
+  G[8] = tmp6 - tmp7;
+  G[9] = tmp8 + tmp9;
+  G[10] = 1 - tmp3 - tmp1;
+  tmp1 = p[5] * sb;
+  tmp2 = p[3] * p[4] * sc;
+  tmp3 = p[4] * sb;
+  tmp4 = p[3] * p[5] * sc;
+  tmp5 = p[3] * sb;
+  tmp6 = p[4] * p[5] * sc;
+  G[3] = (1 - (ra2 + ra3) * sc) * p[0] + (tmp2 - tmp1) * p[1] + (tmp3 + tmp4) * p[2];
+  G[7] = (tmp1 + tmp2) * p[0] + (1 - (ra1 + ra3) * sc) * p[1] + (tmp6 - tmp5) * p[2];
+  G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
+}
+
 // ---- util_SE3_group_to_coeff<T>, utilities.h:149-241 --------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void se3_log(T* p, const T* G) {
@@ -202,6 +259,7 @@ struct Lu6 {
   int rank;
   int pr[6];      // c[k] = b[pr[k]]   == the row transpositions applied in order
   int qd[6];      // x[qd[k]] = c[k]   == the column transpositions applied last-to-first
+  float rdiag[6]; // 1 / U(k,k), for the production kernel's reciprocal back substitution
 };
 
 static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
@@ -244,6 +302,7 @@ static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
   for (int k = 5; k >= 0; --k)
     if (f.coltr[k] != k) { const int t = qc[k]; qc[k] = qc[f.coltr[k]]; qc[f.coltr[k]] = t; }
   for (int j = 0; j < 6; ++j) f.qd[qc[j]] = j;
+  for (int j = 0; j < 6; ++j) f.rdiag[j] = 1.0f / LU(j, j);
 #undef LU
 }
 
@@ -293,6 +352,33 @@ static __device__ __noinline__ void lu6_solve(const Lu6& f, const float* b, floa
   for (int k = 5; k >= 0; --k)
     if (f.coltr[k] != k) { float t = c[k]; c[k] = c[f.coltr[k]]; c[f.coltr[k]] = t; }
   for (int i = 0; i < 6; ++i) x[i] = c[i];
+#undef LU
+}
+
+// Production-kernel variant of lu6_solve_full: the six divisions by the pivots become multiplications by their
+// (correctly rounded, once per level) reciprocals.  Differs from the reference's x / u by at most one ulp per
+// division — far below what the fp32 right-hand side carries — and removes six ~10-deep dependent chains from
+// the code the whole CTA waits for.
+__device__ __forceinline__ void lu6_solve_full_rcp(const Lu6& f, const float* b, float* x) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  float c0 = b[f.pr[0]], c1 = b[f.pr[1]], c2 = b[f.pr[2]], c3 = b[f.pr[3]], c4 = b[f.pr[4]], c5 = b[f.pr[5]];
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  c5 = c5 * f.rdiag[5];
+  c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  c4 = c4 * f.rdiag[4];
+  c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  c3 = c3 * f.rdiag[3];
+  c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  c2 = c2 * f.rdiag[2];
+  c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  c1 = c1 * f.rdiag[1];
+  c0 = c0 - c1 * LU(0, 1);
+  c0 = c0 * f.rdiag[0];
+  x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
 #undef LU
 }
 

@@ -698,6 +698,36 @@ cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream) {
 //  * the cross-warp sums are done by six (21) lanes of warp 0 in parallel before lane 0 solves.
 // Shared memory per CTA: 12 B per template pixel + 64 B per point; four CTAs per SM.
 // ==================================================================================================
+// The six steepest-descent values of a pixel are sd_k = dx*A_k + dy*B_k with (A_k, B_k) constant per POINT
+// (odometer.cpp:317-326).  The production kernel therefore never forms them per pixel: per point it accumulates
+//   J^T r :  ax = sum dx*pdiff, ay = sum dy*pdiff            ->  sum_k += A_k*ax + B_k*ay
+//   Hessian: sxx = sum dx*dx, sxy = sum dx*dy, syy = sum dy*dy -> H_ab += A_a A_b sxx + (A_a B_b + B_a A_b) sxy + B_a B_b syy
+// which is the reference's sum with the distributive law applied (exact in real arithmetic; in fp32 it moves the
+// result by the same ~1e-7 relative as a different summation order does) and cuts the per-pixel arithmetic of the
+// iteration from 34 to 12 flops and of the Hessian from 56 to 6.  The general kernel k_track keeps the per-pixel
+// form and is bit-identical to the reference in sum_mode 1.
+__device__ __forceinline__ void fold_jtr(float* acc, const float* cf, float ax, float ay) {
+  acc[0] = acc[0] + ax * cf[0];
+  acc[1] = acc[1] + ay * cf[1];
+  acc[2] = acc[2] + (ax * cf[2] + ay * cf[3]);
+  acc[3] = acc[3] + (ax * cf[4] + ay * cf[5]);
+  acc[4] = acc[4] + (ax * cf[6] + ay * cf[7]);
+  acc[5] = acc[5] + (ax * cf[8] + ay * cf[9]);
+}
+
+__device__ __forceinline__ void fold_hessian(float* acc, const float* cf, float sxx, float sxy, float syy) {
+  const float A[6] = {cf[0], 0.0f, cf[2], cf[4], cf[6], cf[8]};
+  const float B[6] = {0.0f, cf[1], cf[3], cf[5], cf[7], cf[9]};
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) {
+      acc[k] = acc[k] + ((A[a] * A[b]) * sxx + (A[a] * B[b] + B[a] * A[b]) * sxy + (B[a] * B[b]) * syy);
+      ++k;
+    }
+}
+
 struct FastShared {
   float G[12];
   float p[6];
@@ -806,9 +836,14 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
       bool vis = false;
       PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
       float cf[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) cf[k] = 0.0f;
+      float sxx = 0.0f, sxy = 0.0f, syy = 0.0f;     // sums of dx*dx, dx*dy, dy*dy of the current point
       for (int g = g_lo; g < g_hi; ++g) {
         const int i = g / GPP, gp = g - i * GPP;
         if (i != cur) {
+          fold_hessian(acc, cf, sxx, sxy, syy);
+          sxx = sxy = syy = 0.0f;
           cur = i;
           const float xc = s_Xc[i], yc = s_Yc[i], zc = s_Zc[i];
           const float mx = (xc / zc) * fx + cx, my = (yc / zc) * fy + cy;
@@ -816,7 +851,11 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
           if (vis) {
             pl = patch_place(mx, my, pszd2, width);
             sd_coefs(xc, yc, zc, fx, fy, cf);
-            if (gp == 0 && lane < 10) s_coef[i * 10 + lane] = cf[lane];   // persists for later levels
+            if (gp == 0) {                                                // persists for later levels
+#pragma unroll
+              for (int k = 0; k < 10; ++k)
+                if (lane == k) s_coef[i * 10 + k] = cf[k];
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < 10; ++k) cf[k] = s_coef[i * 10 + k];      // stale coefficients
@@ -852,16 +891,14 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
           }
         }
 #pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          float sd[6];
-          sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);   // own writes: no barrier needed
-          int k = 0;
-#pragma unroll
-          for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b) { acc[k] = acc[k] + sd[a] * sd[b]; ++k; }
+        for (int j = 0; j < KT; ++j) {   // own writes: no barrier needed
+          const float gx = s_gx[ebase + 32 * j], gy = s_gy[ebase + 32 * j];
+          sxx = sxx + gx * gx;
+          sxy = sxy + gx * gy;
+          syy = syy + gy * gy;
         }
       }
+      fold_hessian(acc, cf, sxx, sxy, syy);
 #pragma unroll
       for (int k = 0; k < 21; ++k) {
         const float v = warp_sum(acc[k]);
@@ -892,6 +929,7 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
 
     // ---- iterations --------------------------------------------------------------------------------
     while (S.cont) {
+      const long long t_it0 = trace ? clock64() : 0;   // instrumentation only (trace records [22], [23])
       float Gm[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) Gm[k] = S.G[k];
@@ -903,9 +941,14 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
       bool vis = false;
       PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
       float cf[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) cf[k] = 0.0f;
+      float ax = 0.0f, ay = 0.0f;                    // sums of dx*pdiff, dy*pdiff of the current point
       for (int g = g_lo; g < g_hi; ++g) {
         const int i = g / GPP, gp = g - i * GPP;
         if (i != cur) {
+          fold_jtr(acc, cf, ax, ay);
+          ax = ay = 0.0f;
           cur = i;
           const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];       // project_pt, pose.cpp:307-397
           const float tx = Gm[0] * X + Gm[1] * Y + Gm[2] * Z + Gm[3];
@@ -931,10 +974,8 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
             const float pn = ((pl.w0 * a_ + pl.w1 * b_) + pl.w2 * c_) + pl.w3 * d_;
             c_ = a_; d_ = b_;
             const float pd = s_ref[ebase + 32 * j] - pn;
-            float sd[6];
-            sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;
+            ax = ax + s_gx[ebase + 32 * j] * pd;
+            ay = ay + s_gy[ebase + 32 * j] * pd;
           }
         } else {
 #pragma unroll
@@ -942,36 +983,44 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
             const int q = gp * GE + 32 * j + lane, r = q / PSZ, c = q - r * PSZ;
             const float pn = bilin4(Inew, pl.base + r * width + c, width, pl.w0, pl.w1, pl.w2, pl.w3);
             const float pd = s_ref[ebase + 32 * j] - pn;
-            float sd[6];
-            sd_values(s_gx[ebase + 32 * j], s_gy[ebase + 32 * j], cf, sd);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc[k] = acc[k] + sd[k] * pd;
+            ax = ax + s_gx[ebase + 32 * j] * pd;
+            ay = ay + s_gy[ebase + 32 * j] * pd;
           }
         }
       }
+      fold_jtr(acc, cf, ax, ay);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const float v = warp_sum(acc[k]);
         if (lane == 0) S.part[warp * 24 + k] = v;
       }
       if (lane == 0) S.part[warp * 24 + 6] = (float)nvis;
+      const long long t_par = trace ? clock64() : 0;
       __syncthreads();
       if (warp == 0) {
-        if (lane < 7) {   // 9a. cross-warp sums, fixed order, seven lanes in parallel
-          float s = S.part[lane];
-          for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 24 + lane];
+        const long long t_ser0 = trace ? clock64() : 0;
+        if (lane < 7) {   // 9a. cross-warp sums, fixed order, seven lanes in parallel (loads issued together)
+          float v[8];
+#pragma unroll
+          for (int wv = 0; wv < 8; ++wv) v[wv] = wv < nw ? S.part[wv * 24 + lane] : 0.0f;
+          float s = v[0];
+#pragma unroll
+          for (int wv = 1; wv < 8; ++wv) s = wv < nw ? s + v[wv] : s;
           S.sum[lane] = s;
         }
         __syncwarp();
         if (lane == 0) {
           if (S.lu.rank == 6)
-            lu6_solve_full(S.lu, S.sum, S.dp);     // 9b. odometer.cpp:407
+            lu6_solve_full_rcp(S.lu, S.sum, S.dp); // 9b. odometer.cpp:407
           else
             lu6_solve(S.lu, S.sum, S.dp);
-          float dp[6];
+          float dp[6], pr[6], Gr[12];                // registers: shared-memory operands would be re-read after every store
 #pragma unroll
-          for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; S.p[k] += dp[k]; }   // 10. addpose_se3
-          se3_exp<float>(S.G, S.p);
+          for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; pr[k] = S.p[k] + dp[k]; S.p[k] = pr[k]; }   // 10. addpose_se3
+          Gr[3] = Gr[7] = Gr[11] = 0.0f;
+          se3_exp_f32_series(Gr, pr);
+#pragma unroll
+          for (int k = 0; k < 12; ++k) S.G[k] = Gr[k];
           const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
                                (fabsf(dp[4]) + fabsf(dp[5]));
           if (S.it == 0) S.normdp_init = normdp;
@@ -985,6 +1034,8 @@ __global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
             rec[14] = normdp;
             rec[15] = (float)nv;
             for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+            rec[22] = (float)(clock64() - t_ser0);     // cycles warp 0 spends in the serial section
+            rec[23] = (float)(t_par - t_it0);          // cycles warp 0 spends in the parallel section
           }
           S.npix += (long long)nv * N;
           S.it += 1;

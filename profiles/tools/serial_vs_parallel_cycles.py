@@ -1,0 +1,9 @@
+import sys
+import os; R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
+import numpy as np
+import invcompcamtrack_b200 as ict
+from helpers import make_case, gpu_run
+case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=4096)
+g = gpu_run(ict, case, trace_cap=48)
+tr = g["trace"]; m = tr[...,0] >= 0
+print("records", m.sum(), "serial cycles mean %.0f median %.0f  parallel cycles mean %.0f median %.0f" % (tr[...,22][m].mean(), np.median(tr[...,22][m]), tr[...,23][m].mean(), np.median(tr[...,23][m])))
