@@ -10,6 +10,7 @@
 #include "ict_device.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace ict {
 
@@ -741,10 +742,10 @@ struct FastShared {
   long long npix;
 };
 
-template <int PSZ>
-__global__ void __launch_bounds__(256, 4) k_track_fast(const TrackParams prm) {
+template <int PSZ, int KTMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm) {
   constexpr int N = PSZ * PSZ;                      // pixels per patch
-  constexpr int KT = (N / 32 < 4) ? N / 32 : 4;     // 32-pixel steps per group
+  constexpr int KT = (N / 32 < KTMAX) ? N / 32 : KTMAX;   // 32-pixel steps per group
   constexpr int GE = 32 * KT;                       // pixels per group
   constexpr int GPP = N / GE;                       // groups per point
   extern __shared__ __align__(16) float smem[];
@@ -1065,20 +1066,44 @@ static size_t fast_smem_bytes(const ict_optparam& op, int max_pts) {
   return sizeof(float) * (3 * P * op.novals + 16 * P);
 }
 
-template <int PSZ>
-static cudaError_t launch_track_fast_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
+template <int PSZ, int KTMAX, int MINB>
+static cudaError_t launch_track_fast_v(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_track_fast<PSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_track_fast<PSZ, KTMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_track_fast<PSZ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      e = cudaFuncSetAttribute(k_track_fast<PSZ, KTMAX, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_track_fast<PSZ><<<prm.T, nt, smem, stream>>>(prm);
+  k_track_fast<PSZ, KTMAX, MINB><<<prm.T, nt, smem, stream>>>(prm);
   COUNT_LAUNCH();
   return cudaGetLastError();
+}
+
+template <int PSZ>
+static cudaError_t launch_track_fast_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
+  // Rows per group x CTAs per SM, measured on one B200 with profiles/tools/variant_sweep.sh (psz 32, 8 sequences):
+  //   KT 4/4 CTAs 2.61e11   KT 4/3 CTAs 2.51e11   KT 8/4 2.75e11   KT 8/3 2.66e11   KT 16/4 2.80e11   KT 16/3 2.66e11
+  // pixel-residuals/s: more rows per group put more independent gathers in flight per warp, and four resident CTAs
+  // beat three even though 64 registers spill ~230 B in the per-level precompute.
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("ICT_FAST_VARIANT");   // tuning knob for profiling runs only
+    variant = e ? atoi(e) : 4;
+  }
+  if (PSZ == 32) {
+    switch (variant) {
+      case 0: return launch_track_fast_v<PSZ, 4, 4>(prm, smem, nt, stream);
+      case 1: return launch_track_fast_v<PSZ, 4, 3>(prm, smem, nt, stream);
+      case 2: return launch_track_fast_v<PSZ, 8, 4>(prm, smem, nt, stream);
+      case 3: return launch_track_fast_v<PSZ, 8, 3>(prm, smem, nt, stream);
+      case 5: return launch_track_fast_v<PSZ, 16, 3>(prm, smem, nt, stream);
+      default: return launch_track_fast_v<PSZ, 16, 4>(prm, smem, nt, stream);
+    }
+  }
+  return launch_track_fast_v<PSZ, 4, 4>(prm, smem, nt, stream);
 }
 
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode) {
