@@ -145,16 +145,18 @@ def main():
     ap.add_argument("--cpu-seqs", type=int, default=env_int("ICT_BENCH_CPU_SEQS", 8), help="sequences in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--maxiter", type=int, default=10)
+    ap.add_argument("--ratio", type=float, default=0.01, help="normdp_ratio")
     ap.add_argument("--textures", type=int, default=4, help="distinct textures shared by the sequences (setup time)")
     a = ap.parse_args()
 
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     S, T, P, psz, w, h, lv_f = a.seqs, a.tracks, a.points, a.psz, a.width, a.height, 3
-    op_kw = dict(lv_f=lv_f, lv_l=0, psz=psz, maxiter=10, normdp_ratio=0.01, donorm=0, dopatchnorm=0, maxpttrack=P)
+    op_kw = dict(lv_f=lv_f, lv_l=0, psz=psz, maxiter=a.maxiter, normdp_ratio=a.ratio, donorm=0, dopatchnorm=0, maxpttrack=P)
     config = {"workload": "S=%d synthetic %dx%d frame pairs x %d tracks x %d points x %dx%d patches per GPU, "
-                          "4-level pyramid, maxiter 10, normdp_ratio 0.01 (BASELINE configs[4] per-GPU share)"
-                          % (S, w, h, T, P, psz, psz),
+                          "4-level pyramid, maxiter %d, normdp_ratio %g (BASELINE configs[4] per-GPU share)"
+                          % (S, w, h, T, P, psz, psz, a.maxiter, a.ratio),
               "seqs_per_gpu": S, "tracks_per_seq": T, "points_per_track": P, "psz": psz, "frame": [w, h],
               "levels": lv_f + 1, "l2_policy": "inputs larger than L2: %.0f MB of pyramids + %.0f MB of uint8 frames per step"
               % (S * 2 * 3 * 12.52, S * 2 * w * h / 1e6)}

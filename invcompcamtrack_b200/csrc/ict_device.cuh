@@ -306,6 +306,109 @@ static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
 #undef LU
 }
 
+// Warp-cooperative form of lu6_factor: the SAME full-pivoting elimination (same pivot choice — first maximum in
+// column-major order —, same divisions, same rank-1 updates, hence the same bits), with lane j < 6 holding column j
+// of the matrix in six registers.  The pivot search is a per-lane scan plus a three-step butterfly, the row swap is
+// register renaming under predicates, the column swap and the broadcast of the scaled pivot column are shuffles.
+// Called by all 32 lanes of one warp; Hs = the 21 unique sums in the order of ComputeHessian (odometer.cpp:430-455).
+// The single-thread version costs ~26 000 SM cycles per level on a busy SM (dynamic indexing -> local memory,
+// one long dependent chain) while every other warp of the CTA waits; this one ~2 000.
+__device__ __forceinline__ void lu6_factor_warp(const float* Hs, Lu6& f) {
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  float a[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int p = i < lane ? i : lane, q = i < lane ? lane : i;           // H(i, lane) = Hs[idx(min, max)]
+    const int idx = p * 6 - (p * (p - 1)) / 2 + (q - p);
+    a[i] = lane < 6 ? Hs[idx] : 0.0f;
+  }
+  int nonzero = 6;
+  float maxpivot = 0.0f;
+  int rowtr = 0, coltr = 0;   // lane k keeps transposition k
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (nonzero == 6) {       // uniform across the warp
+      float bv = -1.0f;
+      int bi = k, bl = lane;
+#pragma unroll
+      for (int i = k; i < 6; ++i) {
+        const float v = fabsf(a[i]);
+        if (v > bv) { bv = v; bi = i; }
+      }
+      if (lane < k || lane > 5) bv = -2.0f;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        const int ol = __shfl_xor_sync(FULL, bl, o);
+        if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bi = oi; bl = ol; }
+      }
+      const float biggest = __shfl_sync(FULL, bv, 0);
+      const int pr = __shfl_sync(FULL, bi, 0), pc = __shfl_sync(FULL, bl, 0);
+      if (biggest == 0.0f) {
+        nonzero = k;
+      } else {
+        if (biggest > maxpivot) maxpivot = biggest;
+        if (lane == k) { rowtr = pr; coltr = pc; }
+        // rows k <-> pr (every lane, its own column)
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+          if (pr == i) { const float t = a[k]; a[k] = a[i]; a[i] = t; }
+        // columns k <-> pc
+        const int src = lane == k ? pc : (lane == pc ? k : lane);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a[i] = __shfl_sync(FULL, a[i], src);
+        if (k < 5) {
+          if (lane == k) {
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) a[i] = a[i] / a[k];
+          }
+#pragma unroll
+          for (int i = k + 1; i < 6; ++i) {
+            const float l = __shfl_sync(FULL, a[i], k);
+            if (lane > k && lane < 6) a[i] = a[i] - l * a[k];
+          }
+        }
+      }
+    }
+    if (nonzero != 6 && lane == k && k >= nonzero) { rowtr = k; coltr = k; }
+  }
+  // diagonal, rank, reciprocals
+  float diag = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (lane == i) diag = a[i];
+  const float premult = fabsf(maxpivot) * (1.1920929e-07f * 6.0f);
+  const unsigned ok = __ballot_sync(FULL, lane < nonzero && fabsf(diag) > premult);
+  // index tables of the solve: pr = the row transpositions applied in order to the identity, qc = the column
+  // transpositions applied last-to-first; lane j carries entry j, transposition k comes from lane k
+  int pr = lane, qc = lane;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int r = __shfl_sync(FULL, rowtr, k);
+    const int vk = __shfl_sync(FULL, pr, k), vr = __shfl_sync(FULL, pr, r);
+    if (lane == k) pr = vr; else if (lane == r) pr = vk;
+  }
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+    const int c = __shfl_sync(FULL, coltr, k);
+    const int vk = __shfl_sync(FULL, qc, k), vc = __shfl_sync(FULL, qc, c);
+    if (lane == k) qc = vc; else if (lane == c) qc = vk;
+  }
+  if (lane < 6) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) f.lu[i + 6 * lane] = a[i];
+    f.rowtr[lane] = rowtr;
+    f.coltr[lane] = coltr;
+    f.rdiag[lane] = 1.0f / diag;
+    f.pr[lane] = pr;
+    f.qd[qc] = lane;
+  }
+  if (lane == 0) f.rank = __popc(ok);
+  __syncwarp();
+}
+
 // The same solve as lu6_solve for a full-rank factorisation, as straight-line code: identical operations in
 // identical order (column-oriented unit-lower forward substitution, then upper backward substitution), no loops
 // over run-time bounds and no dynamically indexed locals.  f, b and x live in shared memory.

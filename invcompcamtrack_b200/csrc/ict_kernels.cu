@@ -500,12 +500,8 @@ __global__ void __launch_bounds__(256) k_track(const TrackParams prm) {
       }
     }
     __syncthreads();
+    if (warp == 0) lu6_factor_warp(S.Hsum, S.lu);  // factor once; the solves below repeat Eigen's op order
     if (tid == 0) {
-      float H[36];
-      int k = 0;
-      for (int a = 0; a < 6; ++a)
-        for (int b = a; b < 6; ++b) { H[a + 6 * b] = S.Hsum[k]; H[b + 6 * a] = S.Hsum[k]; ++k; }
-      lu6_factor(H, S.lu);                         // factor once; the solves below repeat Eigen's op order
       S.normdp_init = 1e-10f;                      // odometer.cpp:341-342
       S.normdp = 1e-10f;
       S.it = 0;
@@ -737,7 +733,7 @@ struct FastShared {
   float part[8 * 24];
   float Hsum[21];
   Lu6 lu;
-  float normdp, normdp_init;
+  float normdp, normdp_init, lvl_cycles;
   int cont, it;
   long long npix;
 };
@@ -908,22 +904,24 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
     }
     __syncthreads();
     if (warp == 0) {
+      const long long t_lv0 = trace ? clock64() : 0;
       if (lane < 21) {
-        float s = S.part[lane];
-        for (int wv = 1; wv < nw; ++wv) s = s + S.part[wv * 24 + lane];
+        float v[8];
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v[wv] = wv < nw ? S.part[wv * 24 + lane] : 0.0f;
+        float s = v[0];
+#pragma unroll
+        for (int wv = 1; wv < 8; ++wv) s = wv < nw ? s + v[wv] : s;
         S.Hsum[lane] = s;
       }
       __syncwarp();
+      lu6_factor_warp(S.Hsum, S.lu);                // all 32 lanes; same elimination as Eigen's fullPivLu
       if (lane == 0) {
-        float H[36];
-        int k = 0;
-        for (int a = 0; a < 6; ++a)
-          for (int b = a; b < 6; ++b) { H[a + 6 * b] = S.Hsum[k]; H[b + 6 * a] = S.Hsum[k]; ++k; }
-        lu6_factor(H, S.lu);
         S.normdp_init = 1e-10f;
         S.normdp = 1e-10f;
         S.it = 0;
         S.cont = (0 < op.maxiter) & ((S.normdp / S.normdp_init) > op.normdp_ratio);
+        S.lvl_cycles = (float)(clock64() - t_lv0);
       }
     }
     __syncthreads();
@@ -1010,7 +1008,10 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
           S.sum[lane] = s;
         }
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && prm.dbg_skip_serial) {     // profiling experiment only: how much does the serial section cost?
+          S.it += 1;
+          S.cont = S.it < op.maxiter;
+        } else if (lane == 0) {
           if (S.lu.rank == 6)
             lu6_solve_full_rcp(S.lu, S.sum, S.dp); // 9b. odometer.cpp:407
           else
@@ -1035,6 +1036,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
             rec[14] = normdp;
             rec[15] = (float)nv;
             for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+            rec[21] = S.lvl_cycles;                    // cycles of this level's Hessian sums + LU factorisation
             rec[22] = (float)(clock64() - t_ser0);     // cycles warp 0 spends in the serial section
             rec[23] = (float)(t_par - t_it0);          // cycles warp 0 spends in the parallel section
           }

@@ -246,14 +246,10 @@ __global__ void __launch_bounds__(256) k_big_level_hessian(const BigArgs a) {
 __global__ void __launch_bounds__(256) k_big_level_finish(const BigArgs a, int sl) {
   __shared__ float s_H[21];
   finish_partials<21>(a.w.part, a.w.ncta, s_H);
+  if (threadIdx.x < 32) lu6_factor_warp(s_H, a.w.st->lu);
   if (threadIdx.x == 0) {
     BigState* S = a.w.st;
     const ict_optparam& op = a.prm.op;
-    float H[36];
-    int k = 0;
-    for (int p = 0; p < 6; ++p)
-      for (int q = p; q < 6; ++q) { H[p + 6 * q] = s_H[k]; H[q + 6 * p] = s_H[k]; ++k; }
-    lu6_factor(H, S->lu);
     S->normdp_init = 1e-10f;
     S->normdp = 1e-10f;
     S->it = 0;
@@ -412,14 +408,10 @@ __global__ void __launch_bounds__(192) k_big_level_hessian_exact(const BigArgs a
     s_H[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, Nfull, E);
   }
   __syncthreads();
+  if (tid < 32) lu6_factor_warp(s_H, a.w.st->lu);
   if (tid == 0) {
     BigState* S = a.w.st;
     const ict_optparam& op = a.prm.op;
-    float H[36];
-    int k = 0;
-    for (int p = 0; p < 6; ++p)
-      for (int q = p; q < 6; ++q) { H[p + 6 * q] = s_H[k]; H[q + 6 * p] = s_H[k]; ++k; }
-    lu6_factor(H, S->lu);
     S->normdp_init = 1e-10f;
     S->normdp = 1e-10f;
     S->it = 0;

@@ -6,4 +6,6 @@ from helpers import make_case, gpu_run
 case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=4096)
 g = gpu_run(ict, case, trace_cap=48)
 tr = g["trace"]; m = tr[...,0] >= 0
+m0 = m & (tr[...,1] == 0)
+print("level setup (Hessian sums + LU factor) cycles: median %.0f mean %.0f" % (np.median(tr[...,21][m0]), tr[...,21][m0].mean()))
 print("records", m.sum(), "serial cycles mean %.0f median %.0f  parallel cycles mean %.0f median %.0f" % (tr[...,22][m].mean(), np.median(tr[...,22][m]), tr[...,23][m].mean(), np.median(tr[...,23][m])))
