@@ -260,6 +260,7 @@ struct Lu6 {
   int pr[6];      // c[k] = b[pr[k]]   == the row transpositions applied in order
   int qd[6];      // x[qd[k]] = c[k]   == the column transpositions applied last-to-first
   float rdiag[6]; // 1 / U(k,k), for the production kernel's reciprocal back substitution
+  int qc[6];      // x[j] = c[qc[j]] (inverse of qd), for the lane-parallel solve
 };
 
 static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
@@ -301,7 +302,7 @@ static __device__ __noinline__ void lu6_factor(const float* H, Lu6& f) {
     if (f.rowtr[k] != k) { const int t = f.pr[k]; f.pr[k] = f.pr[f.rowtr[k]]; f.pr[f.rowtr[k]] = t; }
   for (int k = 5; k >= 0; --k)
     if (f.coltr[k] != k) { const int t = qc[k]; qc[k] = qc[f.coltr[k]]; qc[f.coltr[k]] = t; }
-  for (int j = 0; j < 6; ++j) f.qd[qc[j]] = j;
+  for (int j = 0; j < 6; ++j) { f.qd[qc[j]] = j; f.qc[j] = qc[j]; }
   for (int j = 0; j < 6; ++j) f.rdiag[j] = 1.0f / LU(j, j);
 #undef LU
 }
@@ -404,6 +405,7 @@ __device__ __forceinline__ void lu6_factor_warp(const float* Hs, Lu6& f) {
     f.rdiag[lane] = 1.0f / diag;
     f.pr[lane] = pr;
     f.qd[qc] = lane;
+    f.qc[lane] = qc;
   }
   if (lane == 0) f.rank = __popc(ok);
   __syncwarp();
@@ -483,6 +485,33 @@ __device__ __forceinline__ void lu6_solve_full_rcp(const Lu6& f, const float* b,
   c0 = c0 * f.rdiag[0];
   x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
 #undef LU
+}
+
+// lu6_solve_full_rcp spread over six lanes (called by a full warp, rank 6): lane r carries c_r; one shuffle per
+// elimination step broadcasts the pivot row's value.  Same operations per unknown, in the same order, as the
+// straight-line version — about 50 issued instructions instead of 130 on the warp every other warp waits for.
+// Returns x_lane (valid in lanes 0..5).
+__device__ __forceinline__ float lu6_solve_warp_rcp(const Lu6& f, const float* b) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, r = lane < 6 ? lane : 0;
+  float c = b[f.pr[r]];
+  float m[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) m[i] = f.lu[r + 6 * i];     // row r of L\U
+  const float rd = f.rdiag[r];
+  const int qc = f.qc[r];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float ci = __shfl_sync(FULL, c, i);
+    if (r > i) c = c - ci * m[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (r == i) c = c * rd;
+    const float ci = __shfl_sync(FULL, c, i);
+    if (r < i) c = c - ci * m[i];
+  }
+  return __shfl_sync(FULL, c, qc);
 }
 
 // ---- bilinear patch placement, util_getPatch / util_getPatch_grad (utilities.cpp:65-94, 127-157) -----------------

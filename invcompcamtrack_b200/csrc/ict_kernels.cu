@@ -773,6 +773,9 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
   const FrameDesc* fr_ref = prm.frames + rf;
   const FrameDesc* fr_new = prm.frames + nf;
 
+  // the warp that runs the serial sections (Hessian sums + LU, solve + update); env knob for profiling
+  const int swarp = prm.serial_warp_last ? nw - 1 : 0;
+
   // this warp's run of groups
   const int G_all = P * GPP;
   const int gpw = (G_all + nw - 1) / nw;
@@ -903,7 +906,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
       }
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == swarp) {
       const long long t_lv0 = trace ? clock64() : 0;
       if (lane < 21) {
         float v[8];
@@ -996,7 +999,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
       if (lane == 0) S.part[warp * 24 + 6] = (float)nvis;
       const long long t_par = trace ? clock64() : 0;
       __syncthreads();
-      if (warp == 0) {
+      if (warp == swarp) {
         const long long t_ser0 = trace ? clock64() : 0;
         if (lane < 7) {   // 9a. cross-warp sums, fixed order, seven lanes in parallel (loads issued together)
           float v[8];
@@ -1008,14 +1011,17 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
           S.sum[lane] = s;
         }
         __syncwarp();
+        const bool fullrank = S.lu.rank == 6;
+        if (fullrank) {                              // 9b. odometer.cpp:407, six lanes + shuffles
+          const float x = lu6_solve_warp_rcp(S.lu, S.sum);
+          if (lane < 6) S.dp[lane] = x;
+          __syncwarp();
+        }
         if (lane == 0 && prm.dbg_skip_serial) {     // profiling experiment only: how much does the serial section cost?
           S.it += 1;
           S.cont = S.it < op.maxiter;
         } else if (lane == 0) {
-          if (S.lu.rank == 6)
-            lu6_solve_full_rcp(S.lu, S.sum, S.dp); // 9b. odometer.cpp:407
-          else
-            lu6_solve(S.lu, S.sum, S.dp);
+          if (!fullrank) lu6_solve(S.lu, S.sum, S.dp);
           float dp[6], pr[6], Gr[12];                // registers: shared-memory operands would be re-read after every store
 #pragma unroll
           for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; pr[k] = S.p[k] + dp[k]; S.p[k] = pr[k]; }   // 10. addpose_se3
@@ -1146,8 +1152,9 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
   if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
   const long long E = (long long)P * prm.op.novals;
-  const int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
+  int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
   const int mode = (prm.op.dopatchnorm ? 1 : 0) | (prm.sum_mode ? 2 : 0);
+  if (const char* e = getenv("ICT_NT")) nt = atoi(e);   // profiling knob
   if (mode == 0 && !prm.force_general && (prm.op.psz == 8 || prm.op.psz == 16 || prm.op.psz == 32)) {
     const size_t fsm = fast_smem_bytes(prm.op, max_pts);
     switch (prm.op.psz) {

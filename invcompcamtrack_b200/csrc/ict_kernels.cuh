@@ -39,6 +39,7 @@ struct TrackParams {
   float* pt2d_out;                 // [2*total] or null: reference 2-D points at lv_l (Get2DPoints)
   int T;                           // tracks in this launch
   int t0;                          // first track of this launch (index into the per-track arrays)
+  int serial_warp_last;            // profiling knob: run the serial sections on the CTA's last warp instead of warp 0
   int dbg_skip_serial;             // profiling experiment: skip solve/update (results meaningless)
   int force_general;               // 1: always use the general kernel k_track (tests compare the two)
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
