@@ -317,7 +317,7 @@ struct ict_tracker {
   bool have_2d = false;
   int sum_mode = 0;
   int force_general = 0;
-  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
+  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, ticket;
 };
 
 ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2]) {
@@ -338,7 +338,7 @@ ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const
 void ict_tracker_destroy(ict_tracker* tr) {
   if (!tr) return;
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
-                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big};
+                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->ticket};
   for (DevBuf* x : b) x->release();
   delete tr;
 }
@@ -444,7 +444,16 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.dbg_skip_serial = getenv("ICT_DBG_SKIP_SERIAL") ? 1 : 0;
   prm.serial_warp_last = getenv("ICT_SERIAL_WARP_LAST") ? 1 : 0;
   const size_t smem = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode);
-  if (smem <= (size_t)ICT_TRACK_SMEM_LIMIT) {
+  // K2p (two slots per persistent CTA, ict_kernel_pipe.cu) measured 2.67e11 against 3.2e11 pixel-residuals/s for one
+  // track per CTA on B200; it stays selectable for experiments and is covered by a parity test.
+  const int use_pipe = getenv("ICT_PIPE") ? 1 : 0;
+  const bool pipe_ok = use_pipe && !tr->sum_mode && !tr->force_general && !tr->op.dopatchnorm &&
+                       (tr->op.psz == 8 || tr->op.psz == 16 || tr->op.psz == 32) &&
+                       pipe_smem_bytes(tr->op, tr->max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT;
+  if (pipe_ok) {
+    CU(tr->ticket.reserve(sizeof(int)));
+    CU(launch_track_pipe(prm, tr->max_pts, tr->ticket.as<int>(), st));
+  } else if (smem <= (size_t)ICT_TRACK_SMEM_LIMIT) {
     CU(launch_track(prm, tr->max_pts, st));
   } else {
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time

@@ -695,36 +695,6 @@ cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream) {
 //  * the cross-warp sums are done by six (21) lanes of warp 0 in parallel before lane 0 solves.
 // Shared memory per CTA: 12 B per template pixel + 64 B per point; four CTAs per SM.
 // ==================================================================================================
-// The six steepest-descent values of a pixel are sd_k = dx*A_k + dy*B_k with (A_k, B_k) constant per POINT
-// (odometer.cpp:317-326).  The production kernel therefore never forms them per pixel: per point it accumulates
-//   J^T r :  ax = sum dx*pdiff, ay = sum dy*pdiff            ->  sum_k += A_k*ax + B_k*ay
-//   Hessian: sxx = sum dx*dx, sxy = sum dx*dy, syy = sum dy*dy -> H_ab += A_a A_b sxx + (A_a B_b + B_a A_b) sxy + B_a B_b syy
-// which is the reference's sum with the distributive law applied (exact in real arithmetic; in fp32 it moves the
-// result by the same ~1e-7 relative as a different summation order does) and cuts the per-pixel arithmetic of the
-// iteration from 34 to 12 flops and of the Hessian from 56 to 6.  The general kernel k_track keeps the per-pixel
-// form and is bit-identical to the reference in sum_mode 1.
-__device__ __forceinline__ void fold_jtr(float* acc, const float* cf, float ax, float ay) {
-  acc[0] = acc[0] + ax * cf[0];
-  acc[1] = acc[1] + ay * cf[1];
-  acc[2] = acc[2] + (ax * cf[2] + ay * cf[3]);
-  acc[3] = acc[3] + (ax * cf[4] + ay * cf[5]);
-  acc[4] = acc[4] + (ax * cf[6] + ay * cf[7]);
-  acc[5] = acc[5] + (ax * cf[8] + ay * cf[9]);
-}
-
-__device__ __forceinline__ void fold_hessian(float* acc, const float* cf, float sxx, float sxy, float syy) {
-  const float A[6] = {cf[0], 0.0f, cf[2], cf[4], cf[6], cf[8]};
-  const float B[6] = {0.0f, cf[1], cf[3], cf[5], cf[7], cf[9]};
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) {
-      acc[k] = acc[k] + ((A[a] * A[b]) * sxx + (A[a] * B[b] + B[a] * A[b]) * sxy + (B[a] * B[b]) * syy);
-      ++k;
-    }
-}
-
 struct FastShared {
   float G[12];
   float p[6];

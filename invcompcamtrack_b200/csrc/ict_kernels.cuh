@@ -63,6 +63,11 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
+// K2p: two track slots per persistent CTA, serial steps of one slot overlapped with pixel steps of the other.
+// ticket: one device int (zeroed by the launch).  Handles psz 8/16/32 without dopatchnorm, tree sums.
+size_t pipe_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track_pipe(const TrackParams& prm, int max_pts, int* ticket, cudaStream_t stream);
+
 // SetPose only: setpose_se3 + reprojection at lv_l into prm.pt2d_out (one CTA per track)
 cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream);
 

@@ -225,3 +225,20 @@ def test_ncc_scoring(ict, orc):
     assert (ref == -1).any() and (ref > 0.5).any()
     assert np.array_equal(got == -1, ref == -1)
     assert np.abs(got - ref).max() < 2e-5
+
+
+def test_pipelined_kernel_variant(ict, orc, monkeypatch):
+    """ICT_PIPE=1 selects the software-pipelined kernel (two track slots per persistent CTA): same arithmetic as the
+    production kernel, different partial-sum order; checked like it (first-iteration J^T r, oracle spread)."""
+    monkeypatch.setenv("ICT_PIPE", "1")
+    case = make_case(seed=31, ntracks=33)                      # odd count: one CTA ends with a single busy slot
+    g = gpu_run(ict, case)
+    m, spread = check_against_oracle_spread(g, case, orc)
+    assert m["frac_same"] >= 0.93 and m["worst_rot"] <= 1e-5, m
+    case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=300)
+    g = gpu_run(ict, case, trace_cap=48)
+    check_against_oracle_spread(g, case, orc, trace_cap=48)
+    monkeypatch.delenv("ICT_PIPE")
+    g0 = gpu_run(ict, case, trace_cap=48)
+    assert np.array_equal(g["pt2d"], g0["pt2d"])
+    assert np.array_equal(g["trace"][:, 0, 15], g0["trace"][:, 0, 15])
