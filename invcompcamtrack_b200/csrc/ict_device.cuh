@@ -656,4 +656,85 @@ __device__ __forceinline__ float eigen_sum_serial(F v, int N) {
 }
 
 
+
+// Sums NV (<= 24) per-thread values over the 32 lanes of a warp with a "halving" butterfly: at each step a lane keeps
+// one half of its values, sends the other half to its partner and adds what it receives, so the number of live values
+// halves together with the number of lanes that still hold distinct partial sums (27 shuffles for 21 values, 15 for
+// 6, instead of 5 per value).  Fixed order => deterministic.  On return lane L < 32 holds, in out, the total of
+// value index slot_of(L); with NV <= 24 the totals sit in lanes 0,4,8,..: value k in lane (k % 8) * 4 (+ k / 8 picks
+// which of the up to three results the lane holds).  Callers use warp_sum_store below.
+template <int NV>
+__device__ __forceinline__ void warp_sum_store(const float* acc, float* dst /* NV floats, shared */) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  float v[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) v[k] = k < NV ? acc[k] : 0.0f;
+  // offset 16: 24 -> 12
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const float send = up ? v[j] : v[j + 12], keep = up ? v[j + 12] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+  }
+  // offset 8: 12 -> 6
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float send = up ? v[j] : v[j + 6], keep = up ? v[j + 6] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+  }
+  // offset 4: 6 -> 3
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float send = up ? v[j] : v[j + 3], keep = up ? v[j + 3] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+  }
+  // offsets 2, 1: plain butterfly on the three remaining values
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 2);
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 1);
+  }
+  // lane with bits (16,8,4) = (a,b,c) holds values 12a + 6b + 3c + {0,1,2}
+  if ((lane & 3) == 0) {
+    const int base = ((lane >> 4) & 1) * 12 + ((lane >> 3) & 1) * 6 + ((lane >> 2) & 1) * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (base + j < NV) dst[base + j] = v[j];
+  }
+}
+
+// Six values: one halving step (6 -> 3), then a plain butterfly: 15 shuffles instead of 30.
+__device__ __forceinline__ void warp_sum6_store(const float* acc, float* dst /* 6 floats, shared */) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool up = (lane & 16) != 0;
+  float v[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float send = up ? acc[j] : acc[j + 3], keep = up ? acc[j + 3] : acc[j];
+    v[j] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 8);
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 4);
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 2);
+    v[j] = v[j] + __shfl_xor_sync(FULL, v[j], 1);
+  }
+  if ((lane & 15) == 0) {
+    const int base = up ? 3 : 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dst[base + j] = v[j];
+  }
+}
+
 }  // namespace ict

@@ -183,11 +183,7 @@ __device__ __forceinline__ void pipe_pre(const TrackParams& prm, PipeSlot& S, fl
     }
   }
   fold_hessian(acc, cf, sxx, sxy, syy);
-#pragma unroll
-  for (int k = 0; k < 21; ++k) {
-    const float v = warp_sum(acc[k]);
-    if (lane == 0) S.part[warp * 24 + k] = v;
-  }
+  warp_sum_store<21>(acc, &S.part[warp * 24]);
 }
 
 // ---- pixel step ITER: project, new-frame patch, residual, J^T r partials (odometer.cpp:352-404) -----------------
@@ -270,11 +266,7 @@ __device__ __forceinline__ void pipe_iter(const TrackParams& prm, PipeSlot& S, c
     }
   }
   fold_jtr(acc, cf, ax, ay);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float v = warp_sum(acc[k]);
-    if (lane == 0) S.part[warp * 24 + k] = v;
-  }
+  warp_sum6_store(acc, &S.part[warp * 24]);
   if (lane == 0) S.part[warp * 24 + 6] = (float)nvis;
 }
 

@@ -869,11 +869,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
         }
       }
       fold_hessian(acc, cf, sxx, sxy, syy);
-#pragma unroll
-      for (int k = 0; k < 21; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) S.part[warp * 24 + k] = v;
-      }
+      warp_sum_store<21>(acc, &S.part[warp * 24]);
     }
     __syncthreads();
     if (warp == swarp) {
@@ -961,11 +957,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_fast(const TrackParams prm)
         }
       }
       fold_jtr(acc, cf, ax, ay);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) S.part[warp * 24 + k] = v;
-      }
+      warp_sum6_store(acc, &S.part[warp * 24]);
       if (lane == 0) S.part[warp * 24 + 6] = (float)nvis;
       const long long t_par = trace ? clock64() : 0;
       __syncthreads();
