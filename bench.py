@@ -332,7 +332,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_track_dram_bytes_per_launch")
+                traffic = json.load(open(tp))["k_track_dram_bytes_per_track"] * NT   # per launch, like `achieved`
             except Exception:
                 traffic = None
         line = {"metric": "GN pixel-residuals/s", "value": value, "unit": "pixel-residuals/s",
