@@ -86,11 +86,114 @@ __global__ void __launch_bounds__(256) k_pyr_levelN(float* __restrict__ I, float
   dy[o] = gy;
 }
 
+// ---- vectorised forms (4 output pixels per thread, 128-bit stores) ---------------------------------------------
+// Used when the padded row length, the padding and every level width are multiples of 4, so that a group of four
+// output pixels never straddles the image border and all vector accesses are 16-byte aligned.  Same arithmetic.
+__device__ __forceinline__ void ld4(const float* p, float* v) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const unsigned char* p, float* v) {
+  const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+  v[0] = (float)t.x; v[1] = (float)t.y; v[2] = (float)t.z; v[3] = (float)t.w;
+}
+
+template <typename SrcT>
+__global__ void __launch_bounds__(256) k_pyr_level0_v4(const SrcT* __restrict__ src, int w, int h, int pad,
+                                                       float* __restrict__ I, float* __restrict__ dx,
+                                                       float* __restrict__ dy, int64_t plane_stride) {
+  const int sw = w + 2 * pad, sh = h + 2 * pad;
+  const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (X >= sw || Y >= sh) return;
+  const SrcT* s = src + (int64_t)blockIdx.z * w * h;
+  const int x = X - pad, y = Y - pad;
+  const int yc = min(max(y, 0), h - 1);
+  const bool yin = (y >= 0) & (y < h);
+  float vi[4], gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+  if (x < 0 || x >= w) {   // whole group in the left / right padding: replicate for I, zero gradients
+    const float e = (float)s[(int64_t)yc * w + (x < 0 ? 0 : w - 1)];
+    vi[0] = vi[1] = vi[2] = vi[3] = e;
+  } else {
+    const SrcT* row = s + (int64_t)yc * w + x;
+    ld4(row, vi);
+    if (yin) {
+      const float left = x > 0 ? (float)row[-1] : 0.0f, right = x + 4 < w ? (float)row[4] : 0.0f;
+      gx[0] = x > 0 ? vi[1] - left : 0.0f;
+      gx[1] = vi[2] - vi[0];
+      gx[2] = vi[3] - vi[1];
+      gx[3] = x + 4 < w ? right - vi[2] : 0.0f;
+      if (y > 0 && y < h - 1) {
+        float up[4], dn[4];
+        ld4(row - w, up);
+        ld4(row + w, dn);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gy[k] = dn[k] - up[k];
+      }
+    }
+  }
+  const int64_t o = (int64_t)blockIdx.z * plane_stride + (int64_t)Y * sw + X;
+  *reinterpret_cast<float4*>(I + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  *reinterpret_cast<float4*>(dx + o) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+  *reinterpret_cast<float4*>(dy + o) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+}
+
+// four 2x2 means of level l-1 at level-l columns x..x+3 (x multiple of 4), row y: two aligned float4 per source row
+__device__ __forceinline__ void mean4x4(const float* __restrict__ Ip, int swp, int pad, int x, int y, float* v) {
+  const float* r0 = Ip + (int64_t)(2 * y + pad) * swp + 2 * x + pad;
+  float a[8], c[8];
+  ld4(r0, a); ld4(r0 + 4, a + 4);
+  ld4(r0 + swp, c); ld4(r0 + swp + 4, c + 4);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = ((a[2 * k] + a[2 * k + 1]) + (c[2 * k] + c[2 * k + 1])) * 0.25f;
+}
+
+__global__ void __launch_bounds__(256) k_pyr_levelN_v4(float* __restrict__ I, float* __restrict__ dx,
+                                                       float* __restrict__ dy, int64_t plane_stride, int64_t off_prev,
+                                                       int swp, int64_t off_cur, int lw, int lh, int pad) {
+  const int sw = lw + 2 * pad, sh = lh + 2 * pad;
+  const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (X >= sw || Y >= sh) return;
+  const float* Ip = I + (int64_t)blockIdx.z * plane_stride + off_prev;
+  const int x = X - pad, y = Y - pad;
+  const int yc = min(max(y, 0), lh - 1);
+  const bool yin = (y >= 0) & (y < lh);
+  float vi[4], gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+  if (x < 0 || x >= lw) {
+    const float e = mean4(Ip, swp, pad, x < 0 ? 0 : lw - 1, yc);
+    vi[0] = vi[1] = vi[2] = vi[3] = e;
+  } else {
+    mean4x4(Ip, swp, pad, x, yc, vi);
+    if (yin) {
+      gx[0] = x > 0 ? vi[1] - mean4(Ip, swp, pad, x - 1, y) : 0.0f;
+      gx[1] = vi[2] - vi[0];
+      gx[2] = vi[3] - vi[1];
+      gx[3] = x + 4 < lw ? mean4(Ip, swp, pad, x + 4, y) - vi[2] : 0.0f;
+      if (y > 0 && y < lh - 1) {
+        float up[4], dn[4];
+        mean4x4(Ip, swp, pad, x, y - 1, up);
+        mean4x4(Ip, swp, pad, x, y + 1, dn);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gy[k] = dn[k] - up[k];
+      }
+    }
+  }
+  const int64_t o = (int64_t)blockIdx.z * plane_stride + off_cur + (int64_t)Y * sw + X;
+  *reinterpret_cast<float4*>(I + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  *reinterpret_cast<float4*>(dx + o) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+  *reinterpret_cast<float4*>(dy + o) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+}
+
 cudaError_t launch_pyramid(const float* src_f32, const unsigned char* src_u8, int count, int w, int h, int lv_f,
                            int pad, float* I, float* dx, float* dy, int64_t plane_floats,
                            const int64_t* level_off, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
   const dim3 blk(32, 8, 1);
+  // vector path: every level width, the padding and the image base addresses allow aligned groups of four
+  const bool vec = (pad % 4 == 0) && ((w >> lv_f) % 4 == 0) && (plane_floats % 4 == 0) &&
+                   (((uintptr_t)I | (uintptr_t)dx | (uintptr_t)dy) % 16 == 0) &&
+                   (src_u8 ? ((uintptr_t)src_u8 % 4 == 0) : ((uintptr_t)src_f32 % 16 == 0));
   for (int z0 = 0; z0 < count; z0 += 65535) {
     const int zc = min(count - z0, 65535);
     float* Iz = I + (int64_t)z0 * plane_floats;
@@ -98,21 +201,37 @@ cudaError_t launch_pyramid(const float* src_f32, const unsigned char* src_u8, in
     float* dyz = dy + (int64_t)z0 * plane_floats;
     {
       const int sw = w + 2 * pad, sh = h + 2 * pad;
-      const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
-      if (src_u8)
-        k_pyr_level0<unsigned char><<<grd, blk, 0, stream>>>(src_u8 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
-                                                              plane_floats);
-      else
-        k_pyr_level0<float><<<grd, blk, 0, stream>>>(src_f32 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
-                                                      plane_floats);
+      if (vec) {
+        const dim3 grd((sw / 4 + 31) / 32, (sh + 7) / 8, zc);
+        if (src_u8)
+          k_pyr_level0_v4<unsigned char><<<grd, blk, 0, stream>>>(src_u8 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                                   plane_floats);
+        else
+          k_pyr_level0_v4<float><<<grd, blk, 0, stream>>>(src_f32 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                           plane_floats);
+      } else {
+        const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
+        if (src_u8)
+          k_pyr_level0<unsigned char><<<grd, blk, 0, stream>>>(src_u8 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                                plane_floats);
+        else
+          k_pyr_level0<float><<<grd, blk, 0, stream>>>(src_f32 + (int64_t)z0 * w * h, w, h, pad, Iz, dxz, dyz,
+                                                        plane_floats);
+      }
       COUNT_LAUNCH();
     }
     for (int l = 1; l <= lv_f; ++l) {
       const int lw = w >> l, lh = h >> l;
       const int sw = lw + 2 * pad, sh = lh + 2 * pad;
-      const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
-      k_pyr_levelN<<<grd, blk, 0, stream>>>(Iz, dxz, dyz, plane_floats, level_off[l - 1], (w >> (l - 1)) + 2 * pad,
-                                            level_off[l], lw, lh, pad);
+      if (vec) {
+        const dim3 grd((sw / 4 + 31) / 32, (sh + 7) / 8, zc);
+        k_pyr_levelN_v4<<<grd, blk, 0, stream>>>(Iz, dxz, dyz, plane_floats, level_off[l - 1],
+                                                 (w >> (l - 1)) + 2 * pad, level_off[l], lw, lh, pad);
+      } else {
+        const dim3 grd((sw + 31) / 32, (sh + 7) / 8, zc);
+        k_pyr_levelN<<<grd, blk, 0, stream>>>(Iz, dxz, dyz, plane_floats, level_off[l - 1], (w >> (l - 1)) + 2 * pad,
+                                              level_off[l], lw, lh, pad);
+      }
       COUNT_LAUNCH();
     }
   }
