@@ -275,23 +275,57 @@ def main():
         lib = ict.lib()
         v = C.c_void_p
 
-        def step_host():
-            frames.upload_ptr(0, 2 * S, h_frames.data_ptr(), u8=True)
-            rc = lib.ict_tracker_set_points(tracker.h_, NT, v(wl["pt_off"].ctypes.data), v(h_pts.data_ptr()), 0)
-            rc |= lib.ict_track_batch(tracker.h_, frames.h_, v(wl["ref"].ctypes.data), v(wl["new"].ctypes.data),
-                                      v(h_pin.data_ptr()), v(h_pout.data_ptr()), v(h_iters.data_ptr()), None, 0,
-                                      v(h_npix.data_ptr()))
-            if rc:
-                raise ict.IctError(lib.ict_last_error().decode())
+        # The batch goes through the C ABI in chunks of sequences on two streams, one tracker per chunk, so that the
+        # H2D copy of one chunk's frames overlaps the tracking of the previous chunk (ict_*_stream entry points).
+        nchunk = min(4, S)
+        bounds = [(c * S) // nchunk for c in range(nchunk + 1)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        chunk_trackers = [ict.Tracker(op, wl["fc"], wl["cc"], wl["wh"]) for _ in range(nchunk)]
+        chunk_off = []
+        for c in range(nchunk):
+            t0_, t1_ = bounds[c] * T, bounds[c + 1] * T
+            chunk_off.append(np.ascontiguousarray(wl["pt_off"][t0_:t1_ + 1] - wl["pt_off"][t0_]))
 
+        def step_host():
+            for c in range(nchunk):
+                st = v(streams[c % 2].cuda_stream)
+                s0, s1 = bounds[c], bounds[c + 1]
+                t0_, t1_ = s0 * T, s1 * T
+                rc = lib.ict_frames_upload_u8_stream(frames.h_, 2 * s0, 2 * (s1 - s0),
+                                                     v(h_frames.data_ptr() + 2 * s0 * w * h), st)
+                rc |= lib.ict_tracker_set_points_stream(chunk_trackers[c].h_, t1_ - t0_, v(chunk_off[c].ctypes.data),
+                                                        v(h_pts.data_ptr() + 8 * 3 * int(wl["pt_off"][t0_])), st)
+                rc |= lib.ict_track_batch_stream(chunk_trackers[c].h_, frames.h_, v(wl["ref"].ctypes.data + 4 * t0_),
+                                                 v(wl["new"].ctypes.data + 4 * t0_), v(h_pin.data_ptr() + 48 * t0_),
+                                                 v(h_pout.data_ptr() + 48 * t0_), v(h_iters.data_ptr() + 4 * L * t0_),
+                                                 v(h_npix.data_ptr() + 8 * t0_), st)
+                if rc:
+                    raise ict.IctError(lib.ict_last_error().decode())
+
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record()
+            for st_ in streams:
+                st_.wait_event(ev)
+
+        def join():
+            for st_ in streams:
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                torch.cuda.current_stream().wait_event(ev)
+
+        fork()
         for _ in range(min(a.warmup, 2)):
             step_host()
+        join()
         barrier()
         t0 = time.perf_counter()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        fork()
         for _ in range(a.steps):
             step_host()
+        join()
         f1.record()
         barrier()
         wall = time.perf_counter() - t0

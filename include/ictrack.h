@@ -165,6 +165,16 @@ int ict_tracker_reproject(ict_tracker* tr, const double* p_in, float* pt2d_out);
  * out float[2*n_t] per track at 2*pt_off[t]: x block then y block. Host buffer. */
 int ict_tracker_get_2dpoints(ict_tracker* tr, float* out);
 
+/* ---- stream-ordered host-buffer variants ------------------------------------------------------------------------
+ * Same work as ict_frames_upload_u8 / ict_tracker_set_points / ict_track_batch, enqueued on the caller's
+ * cudaStream_t without a final synchronisation, so that the H2D copies of one chunk of a batch overlap the tracking
+ * of another (use one tracker per chunk; host buffers should be pinned and must stay valid until the stream has
+ * been synchronised; outputs are valid after that).  No trace, no in-place centring of the caller's points. */
+int ict_frames_upload_u8_stream(ict_frames* fs, int first, int count, const unsigned char* imgs, void* stream);
+int ict_tracker_set_points_stream(ict_tracker* tr, int T, const int64_t* pt_off, const double* pts, void* stream);
+int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref_frame, const int* new_frame,
+                           const double* p_in, double* p_out, int* iters, int64_t* npixres, void* stream);
+
 /* ---- single-pair convenience == the body of run_io_reprojection_test.cpp:157-224 -------------------
  * imgA/imgB: host h*w floats (uint8-valued as produced by imread+convertTo).  pt3d: X block, Y block, Z block
  * (npts each; written if op->donorm, like the reference).  iters/trace may be NULL. */

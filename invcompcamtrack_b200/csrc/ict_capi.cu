@@ -283,6 +283,20 @@ int ict_frames_upload_planes(ict_frames* fs, int frame, const float* I, const fl
   return ICT_OK;
 }
 
+int ict_frames_upload_u8_stream(ict_frames* fs, int first, int count, const unsigned char* imgs, void* stream) {
+  if (frames_range_ok(fs, first, count)) return ICT_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = (size_t)fs->w * fs->h;
+  // one staging area for the whole store, each frame at its own offset: chunks in flight never share bytes
+  if (fs->stage.cap < per * fs->nframes) {
+    CU(cudaDeviceSynchronize());
+    CU(fs->stage.reserve(per * fs->nframes));
+  }
+  unsigned char* dst = fs->stage.as<unsigned char>() + per * first;
+  CU(cudaMemcpyAsync(dst, imgs, per * count, cudaMemcpyHostToDevice, st));
+  return frames_build(fs, first, count, nullptr, dst, st);
+}
+
 int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy) {
   if (frames_range_ok(fs, frame, 1)) return ICT_ERR_BAD_ARG;
   if (fs->view) return fail(ICT_ERR_BAD_ARG, "ict_frames_download: a view store owns no pixels");
@@ -383,6 +397,30 @@ int ict_tracker_set_points(ict_tracker* tr, int T, const int64_t* pt_off, double
   CU(launch_set_points(T, tr->pt_off.as<int64_t>(), tr->pts.as<double>(), mut ? tr->pts.as<double>() : nullptr,
                        tr->pt3d.as<float>(), tr->norm.as<double>(), tr->op.donorm, tr->op.maxpttrack, max_pts, 0));
   if (mut) CU(cudaMemcpy(pts, tr->pts.p, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost));
+  tr->T = T;
+  tr->total = total;
+  tr->max_pts = max_pts;
+  tr->h_off.assign(pt_off, pt_off + T + 1);
+  tr->have_2d = false;
+  return ICT_OK;
+}
+
+int ict_tracker_set_points_stream(ict_tracker* tr, int T, const int64_t* pt_off, const double* pts, void* stream) {
+  if (!tr || T <= 0 || !pt_off || !pts) return fail(ICT_ERR_BAD_ARG, "ict_tracker_set_points_stream: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = pt_off[T];
+  int max_pts = 0;
+  for (int t = 0; t < T; ++t) {
+    const int64_t n = pt_off[t + 1] - pt_off[t];
+    if (n < 0 || n > 0x7fffffff) return fail(ICT_ERR_BAD_ARG, "pt_off must be non-decreasing");
+    if (n > max_pts) max_pts = (int)n;
+  }
+  if (tracker_reserve(tr, T, total)) return ICT_ERR_CUDA;
+  CU(tr->pts.reserve(sizeof(double) * 3 * (size_t)(total ? total : 1)));
+  CU(cudaMemcpyAsync(tr->pt_off.p, pt_off, sizeof(int64_t) * (size_t)(T + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(tr->pts.p, pts, sizeof(double) * 3 * (size_t)total, cudaMemcpyHostToDevice, st));
+  CU(launch_set_points(T, tr->pt_off.as<int64_t>(), tr->pts.as<double>(), nullptr, tr->pt3d.as<float>(),
+                       tr->norm.as<double>(), tr->op.donorm, tr->op.maxpttrack, max_pts, st));
   tr->T = T;
   tr->total = total;
   tr->max_pts = max_pts;
@@ -518,6 +556,33 @@ int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame,
     CU(cudaMemcpyAsync(trace, tr->trace.p, sizeof(float) * ICT_TRACE_FLOATS * (size_t)T * trace_cap,
                        cudaMemcpyDeviceToHost, 0));
   CU(cudaStreamSynchronize(0));
+  return ICT_OK;
+}
+
+int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref_frame, const int* new_frame,
+                           const double* p_in, double* p_out, int* iters, int64_t* npixres, void* stream) {
+  if (!tr || !fs || !ref_frame || !new_frame || !p_in || !p_out) return fail(ICT_ERR_BAD_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = tr->T;
+  if (T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
+  if (track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode) > (size_t)ICT_TRACK_SMEM_LIMIT)
+    return fail(ICT_ERR_UNSUPPORTED, "stream variant handles tracks that fit one CTA");
+  const int L = tr->op.lv_f - tr->op.lv_l + 1;
+  CU(tr->rf.reserve(sizeof(int) * (size_t)T));
+  CU(tr->nf.reserve(sizeof(int) * (size_t)T));
+  CU(tr->p_in.reserve(sizeof(double) * 6 * (size_t)T));
+  CU(tr->p_out.reserve(sizeof(double) * 6 * (size_t)T));
+  CU(tr->iters.reserve(sizeof(int) * (size_t)T * L));
+  CU(tr->npix.reserve(sizeof(long long) * (size_t)T));
+  CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, st));
+  const int rc = run_tracks(tr, fs, tr->rf.as<int>(), tr->nf.as<int>(), -1, -1, tr->p_in.as<double>(),
+                            tr->p_out.as<double>(), tr->iters.as<int>(), nullptr, 0, tr->npix.as<long long>(), st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(p_out, tr->p_out.p, sizeof(double) * 6 * (size_t)T, cudaMemcpyDeviceToHost, st));
+  if (iters) CU(cudaMemcpyAsync(iters, tr->iters.p, sizeof(int) * (size_t)T * L, cudaMemcpyDeviceToHost, st));
+  if (npixres) CU(cudaMemcpyAsync(npixres, tr->npix.p, sizeof(long long) * (size_t)T, cudaMemcpyDeviceToHost, st));
   return ICT_OK;
 }
 
