@@ -1,0 +1,589 @@
+// ict_kernel_v2.cu — K2v2, the production form of SetPose + TrackPose for 32x32 patches (tree reductions, no patch
+// normalisation): one 256-thread CTA per track, all levels and iterations on device, like k_track_fast
+// (ict_kernels.cu), rebuilt around what ncu showed of that kernel (profiles/r01_k_track_fast_ncu_summary.txt):
+// 60 issued instructions per pixel-residual and a ~3000-cycle single-lane section per iteration behind a barrier.
+//
+//  * Template layout.  (pat_ref, pat_dx, pat_dy) stay resident in shared memory (12 B per template pixel), but four
+//    consecutive ROWS of one column are one float4: a lane (= patch column) reads the template of four pixels with
+//    three conflict-free LDS.128 instead of twelve LDS.32.
+//  * Pixel loop.  Per pixel-residual: two read-only loads (the row and its left-shifted copy; the row above is
+//    carried in registers), the bilinear sample as one multiply and three EXPLICIT fused multiply-adds in the
+//    reference's association order w0*a + w1*b + w2*c + w3*d (utilities.cpp:107), the residual, and two fused
+//    multiply-adds into sum(dx*r), sum(dy*r) of the point (the factorised steepest-descent sums of k_track_fast,
+//    ict_device.cuh fold_jtr).  About 12 instructions.  The file is compiled with -fmad=false like the rest of the
+//    library: everything that decides a pixel INDEX (projection, ceil/floor placement, bounds tests) and the
+//    template itself keep the reference's unfused roundings; fused operations appear only where written as fmaf().
+//  * Per point, not per warp: the new-frame placement (project_pt + util_getPatch's ceil/floor/weights) of every
+//    point is computed once per iteration by the lanes of the serial warp right after the pose update, and the
+//    pixel warps read it back (two LDS.128) instead of each re-deriving it (two IEEE divisions and ~60 more
+//    instructions per warp per iteration).  Warps reduce only (sum dx*r, sum dy*r) — 10 shuffles — and the six
+//    J^T r entries are formed from the per-point sums by six lanes.
+//  * Serial section.  Six lanes fold the partial sums directly in the row order of the LU factorisation; lane 0
+//    runs the straight-line forward/backward substitution on factors every lane prefetched as float4 before the
+//    sums arrive, updates the pose (additive, pose.cpp:116-129), evaluates exp (double Horner series,
+//    ict_device.cuh) and the stop rule; then lanes i < P project the points for the next iteration.
+//
+// Reference semantics kept: min two iterations per level, centre-only inclusive bounds test, stale
+// template/coefficients of points that leave the reference image at a finer level, new-frame-invisible points
+// dropping out of J^T r but staying in H, additive se(3) update.  Parity class = that of k_track_fast: J^T r on
+// identical inputs within ~1e-7 of sum|sd*r|; trajectories within the spread of the reference's own summation
+// orders (tests/test_gpu_parity.py).  Bit-exact parity is k_track<PSZ, 2> (sum_mode 1).
+#include "ict_kernels.cuh"
+#include "ict_device.cuh"
+
+#include <cstdlib>
+
+namespace ict {
+
+void count_launch_external();
+
+struct __align__(16) V2Shared {
+  float Hinv[64];          // rows of M (delta_p = M * J^T r; H^-1 at full rank), 8 floats per row, rows/columns 6, 7 zero
+  float G[12];
+  float p[8];
+  float Hsum[24];
+  Lu6 f;
+  float lvl_cycles, gather_cycles;
+  int cont, it;
+};
+
+__device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// project_pt (pose.cpp:307-397) of one point at level intrinsics (fx, fy, cx, cy) + util_getPatch placement
+// (utilities.cpp:65-94): the reference's operation order, no fused operations.  Writes {base, vis, -, -}, {w0..w3}.
+__device__ __forceinline__ int place_point(const float* G, float X, float Y, float Z, float fx, float fy, float cx,
+                                           float cy, float swo, float sho, int width, float4* dst) {
+  const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];
+  const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
+  const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
+  const float mx = (tx / tz) * fx + cx, my = (ty / tz) * fy + cy;
+  const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);   // odometer.cpp:369-371 (NaN -> outside)
+  PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
+  if (vis) pl = patch_place(mx, my, 16, width);
+  dst[0] = make_float4(__int_as_float(pl.base), __int_as_float(vis), 0.0f, 0.0f);
+  dst[1] = make_float4(pl.w0, pl.w1, pl.w2, pl.w3);
+  return vis;
+}
+
+// Column `col` of the matrix M with delta_p = M * b, b = J^T r, that Eigen's FullPivLU::solve applies
+// (odometer.cpp:514): c = P b, unit-lower forward substitution, upper backward substitution on the leading
+// rank x rank block only, the other unknowns zero, x = Q c.  For rank 6 M is H^-1; for a rank-deficient Hessian it
+// is Eigen's truncated solve — linear in b either way, so it can be tabulated once per level by solving for the six
+// unit vectors (lanes 0..5, col = lane) with the straight-line substitution of ict_device.cuh (lu6_solve_full_rcp:
+// same elimination order, reciprocal pivots).  x_j is written to out[8 * j].
+__device__ __forceinline__ void lu6_solve_matrix_column(const Lu6& f, int col, float* out) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  const int rank = f.rank;
+  float c0 = f.pr[0] == col ? 1.0f : 0.0f, c1 = f.pr[1] == col ? 1.0f : 0.0f, c2 = f.pr[2] == col ? 1.0f : 0.0f;
+  float c3 = f.pr[3] == col ? 1.0f : 0.0f, c4 = f.pr[4] == col ? 1.0f : 0.0f, c5 = f.pr[5] == col ? 1.0f : 0.0f;
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  if (rank > 5) {
+    c5 = c5 * f.rdiag[5];
+    c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  } else c5 = 0.0f;
+  if (rank > 4) {
+    c4 = c4 * f.rdiag[4];
+    c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  } else c4 = 0.0f;
+  if (rank > 3) {
+    c3 = c3 * f.rdiag[3];
+    c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  } else c3 = 0.0f;
+  if (rank > 2) {
+    c2 = c2 * f.rdiag[2];
+    c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  } else c2 = 0.0f;
+  if (rank > 1) {
+    c1 = c1 * f.rdiag[1];
+    c0 = c0 - c1 * LU(0, 1);
+  } else c1 = 0.0f;
+  c0 = rank > 0 ? c0 * f.rdiag[0] : 0.0f;
+  out[8 * f.qd[0]] = c0; out[8 * f.qd[1]] = c1; out[8 * f.qd[2]] = c2;
+  out[8 * f.qd[3]] = c3; out[8 * f.qd[4]] = c4; out[8 * f.qd[5]] = c5;
+#undef LU
+}
+
+// the reference's float exp for the two rare branches (Taylor for sigma <= 1e-4, library sincos beyond pi/4)
+static __device__ __noinline__ void se3_exp_rare(float* G, const float* p) { se3_exp<float>(G, p); }
+
+// util_SE3_coeff_to_group<float> (utilities.h:84-145) on register operands, every lane of the serial warp alike.
+// sa = sin(s)/s, sb = (1-cos s)/s^2, sc = (s-sin s)/s^3 are even power series in z = s*s = |omega|^2; for
+// 1e-8 < z <= (pi/4)^2 they are evaluated by a six-term fused Horner scheme in fp32 directly from z (truncation
+// < 1e-11; the result is within one float ulp of the reference's double-evaluated quotient narrowed to float, and
+// needs neither the square root nor double arithmetic on the critical path of the iteration).  Outside that range
+// (the reference's Taylor branch below sigma = 1e-4, or a rotation beyond 45 degrees per pose) the reference's
+// own formula runs.  The rotation and translation blocks follow the reference's unfused operation order.
+// sG / sp: shared-memory copies of G and p (sp already holds the new coefficients) for the rare branch, which one
+// lane runs through the noinline reference formula so that G itself never has its address taken (registers).
+__device__ __forceinline__ void se3_exp_regs(float* G, float p0, float p1, float p2, float p3, float p4, float p5,
+                                             float* sG, const float* sp) {
+  const float ra1 = p3 * p3, ra2 = p4 * p4, ra3 = p5 * p5;
+  const float z = ra1 + ra2 + ra3;
+  if (!(z > 1.0000001e-8f) || z > 0.61685f) {   // uniform across the warp
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) se3_exp_rare(sG, sp);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 12; ++k) G[k] = sG[k];
+    return;
+  }
+  float sa = -2.5052108385441720e-08f, sb = -2.0876756987868100e-09f, sc = -1.6059043836821613e-10f;
+  sa = fmaf(sa, z, 2.7557319223985893e-06f);  sb = fmaf(sb, z, 2.7557319223985888e-07f);  sc = fmaf(sc, z, 2.5052108385441720e-08f);
+  sa = fmaf(sa, z, -1.9841269841269841e-04f); sb = fmaf(sb, z, -2.4801587301587302e-05f); sc = fmaf(sc, z, -2.7557319223985893e-06f);
+  sa = fmaf(sa, z, 8.3333333333333332e-03f);  sb = fmaf(sb, z, 1.3888888888888889e-03f);  sc = fmaf(sc, z, 1.9841269841269841e-04f);
+  sa = fmaf(sa, z, -1.6666666666666666e-01f); sb = fmaf(sb, z, -4.1666666666666664e-02f); sc = fmaf(sc, z, -8.3333333333333332e-03f);
+  sa = fmaf(sa, z, 1.0f);                     sb = fmaf(sb, z, 0.5f);                     sc = fmaf(sc, z, 1.6666666666666666e-01f);
+  float tmp1 = ra2 * sb;
+  float tmp2 = ra3 * sb;
+  float tmp3 = ra1 * sb;
+  float tmp4 = p3 * p4 * sb;
+  float tmp5 = p5 * sa;
+  float tmp6 = p3 * p5 * sb;
+  float tmp7 = p4 * sa;
+  float tmp8 = p3 * sa;
+  float tmp9 = p4 * p5 * sb;
+  G[0] = 1 - tmp1 - tmp2;
+  G[1] = tmp4 - tmp5;
+  G[2] = tmp7 + tmp6;
+  G[4] = tmp5 + tmp4;
+  G[5] = 1 - tmp3 - tmp2;
+  G[6] = tmp9 - tmp8;
+  G[8] = tmp6 - tmp7;
+  G[9] = tmp8 + tmp9;
+  G[10] = 1 - tmp3 - tmp1;
+  tmp1 = p5 * sb;
+  tmp2 = p3 * p4 * sc;
+  tmp3 = p4 * sb;
+  tmp4 = p3 * p5 * sc;
+  tmp5 = p3 * sb;
+  tmp6 = p4 * p5 * sc;
+  G[3] = (1 - (ra2 + ra3) * sc) * p0 + (tmp2 - tmp1) * p1 + (tmp3 + tmp4) * p2;
+  G[7] = (tmp1 + tmp2) * p0 + (1 - (ra1 + ra3) * sc) * p1 + (tmp6 - tmp5) * p2;
+  G[11] = (tmp4 - tmp3) * p0 + (tmp5 + tmp6) * p1 + (1 - (ra1 + ra2) * sc) * p2;
+}
+
+template <int KT, int MINB, bool TRACE>
+__global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
+  constexpr int N = 1024;                 // pixels per patch (psz 32)
+  constexpr int GPP = 32 / KT;            // groups (KT rows, lane = column) per point
+  constexpr int RQ = KT / 4;              // float4 row-quads per group
+  extern __shared__ __align__(16) float smem[];
+  __shared__ V2Shared S;
+
+  const int t = blockIdx.x + prm.t0;
+  const ict_optparam& op = prm.op;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int64_t off = prm.pt_off[t];
+  const int n_in = (int)(prm.pt_off[t + 1] - off);
+  const int P = min(n_in, op.maxpttrack);
+  const int E = P * N;
+  const int G_all = P * GPP;
+  const bool donorm = op.donorm != 0;
+
+  // ---- shared-memory carve-up: template planes as float4 row-quads, then the per-point block ---------------------
+  float4* s_ref4 = reinterpret_cast<float4*>(smem);          // [P][8][32] : rows 4q..4q+3 of column c
+  float4* s_gx4 = s_ref4 + E / 4;
+  float4* s_gy4 = s_gx4 + E / 4;
+  float4* s_rpl = s_gy4 + E / 4;                             // [P][2] reference placement {base,vis,-,-},{w0..w3}
+  float4* s_npl = s_rpl + 2 * P;                             // [P][2] new-frame placement of the coming iteration
+  float4* s_hpart = s_npl + 2 * P;                           // [G_all] {sum dx*dx, sum dx*dy, sum dy*dy, -}
+  float2* s_part = reinterpret_cast<float2*>(s_hpart + G_all);   // [2][G_all] {sum dx*r, sum dy*r}, double-buffered
+  float* s_AB = reinterpret_cast<float*>(s_part + 2 * G_all);    // [P][12]: A_0..A_5, B_0..B_5 (sd_k = dx*A_k + dy*B_k)
+  float* s_X = s_AB + 12 * P;                                // per point: world X Y Z, reference-camera Xc Yc Zc
+  float* s_Y = s_X + P;
+  float* s_Z = s_Y + P;
+  float* s_Xc = s_Z + P;
+  float* s_Yc = s_Xc + P;
+  float* s_Zc = s_Yc + P;
+
+  const int rf = prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref;
+  const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
+  const FrameDesc* fr_ref = prm.frames + rf;
+  const FrameDesc* fr_new = prm.frames + nf;
+  const int swarp = prm.serial_warp_last ? nw - 1 : 0;
+
+  // ---- ResetOdometer (odometer.cpp:580-609) + points -----------------------------------------------------------------
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < 3 * E / 4; e += nt) s_ref4[e] = z4;
+    const float* q = prm.pt3d + 3 * off;
+    for (int i = tid; i < P; i += nt) {
+      s_X[i] = q[i];
+      s_Y[i] = q[n_in + i];
+      s_Z[i] = q[2 * (int64_t)n_in + i];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s_AB[i * 12 + k] = 0.0f;
+    }
+  }
+  if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
+  __syncthreads();
+  for (int i = tid; i < P; i += nt) {   // project_pt_save_rotated, pose.cpp:400-488
+    const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
+    const float xc = S.G[0] * X + S.G[1] * Y + S.G[2] * Z + S.G[3];
+    const float yc = S.G[4] * X + S.G[5] * Y + S.G[6] * Z + S.G[7];
+    const float zc = S.G[8] * X + S.G[9] * Y + S.G[10] * Z + S.G[11];
+    s_Xc[i] = xc;
+    s_Yc[i] = yc;
+    s_Zc[i] = zc;
+    if (prm.pt2d_out) {                 // Get2DPoints(): pt2d[lv_l], odometer.h:30
+      const int l = op.lv_l;
+      prm.pt2d_out[2 * off + i] = (xc / zc) * prm.cam.fx[l] + prm.cam.cx[l];
+      prm.pt2d_out[2 * off + n_in + i] = (yc / zc) * prm.cam.fy[l] + prm.cam.cy[l];
+    }
+  }
+  __syncthreads();
+
+  float* trace = TRACE && prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
+  int trace_n = 0;
+  // state of the serial warp, identical in all its lanes unless noted
+  float pk = 0.0f;              // lane (k + 8j) carries pose coefficient k (0 for k = 6, 7)
+  float normdp_init = 1e-10f;
+  int nv = 0;                   // points visible in the new frame at the placements of the coming iteration
+  int nvsum = 0;                // sum of nv over all iterations done: pixel-residuals = nvsum * 1024
+  if (warp == swarp) pk = (lane & 7) < 6 ? S.p[lane & 7] : 0.0f;
+
+  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+    const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
+    const float swo = prm.cam.swo[sl], sho = prm.cam.sho[sl];
+    const int width = prm.cam.width[sl];
+    const float* __restrict__ Iref = fr_ref->I[sl];
+    const float* __restrict__ Dxr = fr_ref->dx[sl];
+    const float* __restrict__ Dyr = fr_ref->dy[sl];
+    const float* __restrict__ Inew = fr_new->I[sl];
+
+    const long long t_g0 = TRACE ? clock64() : 0;
+    // ---- 4a. per point: reference placement + steepest-descent coefficients (odometer.cpp:268-279, 306-326) ------
+    for (int i = tid; i < P; i += nt) {
+      const float xc = s_Xc[i], yc = s_Yc[i], zc = s_Zc[i];
+      const float mx = (xc / zc) * fx + cx, my = (yc / zc) * fy + cy;   // pt2d[sl][i]
+      const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
+      PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
+      if (vis) {
+        pl = patch_place(mx, my, 16, width);
+        float c[10];
+        sd_coefs(xc, yc, zc, fx, fy, c);
+        float* ab = s_AB + i * 12;       // stale coefficients survive when the point is out of view
+        ab[0] = c[0]; ab[1] = 0.0f; ab[2] = c[2]; ab[3] = c[4]; ab[4] = c[6]; ab[5] = c[8];
+        ab[6] = 0.0f; ab[7] = c[1]; ab[8] = c[3]; ab[9] = c[5]; ab[10] = c[7]; ab[11] = c[9];
+      }
+      s_rpl[2 * i] = make_float4(__int_as_float(pl.base), __int_as_float(vis), 0.0f, 0.0f);
+      s_rpl[2 * i + 1] = make_float4(pl.w0, pl.w1, pl.w2, pl.w3);
+    }
+    __syncthreads();
+
+    // ---- 4b+6a. template gather (util_getPatch_grad, utilities.cpp:115-189: unfused, reference order) and the
+    //      per-group sums of dx*dx, dx*dy, dy*dy ---------------------------------------------------------------------
+    for (int g = warp; g < G_all; g += nw) {
+      const int i = g / GPP, gp = g - i * GPP;
+      const float4 pa = s_rpl[2 * i], pw = s_rpl[2 * i + 1];
+      const int tq = (i * 8 + gp * RQ) * 32 + lane;
+      float sxx = 0.0f, sxy = 0.0f, syy = 0.0f;
+      if (__float_as_int(pa.y)) {
+        const int o0 = __float_as_int(pa.x) + (gp * KT) * width + lane;
+        const float* pI = Iref + o0;
+        const float* pX = Dxr + o0;
+        const float* pY = Dyr + o0;
+        float ci = __ldg(pI - width), di = __ldg(pI - width - 1);
+        float cxx = __ldg(pX - width), dxx = __ldg(pX - width - 1);
+        float cyy = __ldg(pY - width), dyy = __ldg(pY - width - 1);
+#pragma unroll
+        for (int jq = 0; jq < RQ; ++jq) {
+          float r[4], gx[4], gy[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ai = __ldg(pI), bi = __ldg(pI - 1);
+            const float ax_ = __ldg(pX), bx_ = __ldg(pX - 1);
+            const float ay_ = __ldg(pY), by_ = __ldg(pY - 1);
+            pI += width; pX += width; pY += width;
+            r[j] = ((pw.x * ai + pw.y * bi) + pw.z * ci) + pw.w * di;
+            gx[j] = ((pw.x * ax_ + pw.y * bx_) + pw.z * cxx) + pw.w * dxx;
+            gy[j] = ((pw.x * ay_ + pw.y * by_) + pw.z * cyy) + pw.w * dyy;
+            ci = ai; di = bi; cxx = ax_; dxx = bx_; cyy = ay_; dyy = by_;
+            sxx = fmaf(gx[j], gx[j], sxx);
+            sxy = fmaf(gx[j], gy[j], sxy);
+            syy = fmaf(gy[j], gy[j], syy);
+          }
+          s_ref4[tq + jq * 32] = make_float4(r[0], r[1], r[2], r[3]);
+          s_gx4[tq + jq * 32] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+          s_gy4[tq + jq * 32] = make_float4(gy[0], gy[1], gy[2], gy[3]);
+        }
+      } else {                           // out of the reference image: the previous level's template stays
+#pragma unroll
+        for (int jq = 0; jq < RQ; ++jq) {
+          const float4 gx = s_gx4[tq + jq * 32], gy = s_gy4[tq + jq * 32];
+          sxx = fmaf(gx.x, gx.x, sxx); sxy = fmaf(gx.x, gy.x, sxy); syy = fmaf(gy.x, gy.x, syy);
+          sxx = fmaf(gx.y, gx.y, sxx); sxy = fmaf(gx.y, gy.y, sxy); syy = fmaf(gy.y, gy.y, syy);
+          sxx = fmaf(gx.z, gx.z, sxx); sxy = fmaf(gx.z, gy.z, sxy); syy = fmaf(gy.z, gy.z, syy);
+          sxx = fmaf(gx.w, gx.w, sxx); sxy = fmaf(gx.w, gy.w, sxy); syy = fmaf(gy.w, gy.w, syy);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sxx = sxx + __shfl_xor_sync(0xffffffffu, sxx, o);
+        sxy = sxy + __shfl_xor_sync(0xffffffffu, sxy, o);
+        syy = syy + __shfl_xor_sync(0xffffffffu, syy, o);
+      }
+      if (lane == 0) s_hpart[g] = make_float4(sxx, sxy, syy, 0.0f);
+    }
+    __syncthreads();
+
+    // ---- 6b. Hessian from the per-point sums, LU factorisation, first placement -----------------------------------
+    if (warp == swarp) {
+      const long long t_lv0 = TRACE ? clock64() : 0;
+      if (TRACE && lane == 0) S.gather_cycles = (float)(t_lv0 - t_g0);
+      if (lane < 21) {
+        int a = 0, b = 0;                // lane-th pair (a <= b) in the order of ComputeHessian (odometer.cpp:430-455)
+        {
+          int k = lane, len = 6;
+          while (k >= len) { k -= len; --len; ++a; }
+          b = a + k;
+        }
+        float h = 0.0f;
+        for (int i = 0; i < P; ++i) {
+          float sxx = 0.0f, sxy = 0.0f, syy = 0.0f;
+          for (int q = 0; q < GPP; ++q) {
+            const float4 v = s_hpart[i * GPP + q];
+            sxx = q ? sxx + v.x : v.x;
+            sxy = q ? sxy + v.y : v.y;
+            syy = q ? syy + v.z : v.z;
+          }
+          const float* ab = s_AB + i * 12;
+          const float Aa = ab[a], Ab = ab[b], Ba = ab[6 + a], Bb = ab[6 + b];
+          h = h + ((Aa * Ab) * sxx + (Aa * Bb + Ba * Ab) * sxy + (Ba * Bb) * syy);
+        }
+        S.Hsum[lane] = h;
+      }
+      __syncwarp();
+      lu6_factor_warp(S.Hsum, S.f);      // all 32 lanes; same elimination (and rank decision) as Eigen's fullPivLu
+      S.Hinv[lane] = 0.0f;
+      S.Hinv[32 + lane] = 0.0f;
+      __syncwarp();
+      if (lane < 6) lu6_solve_matrix_column(S.f, lane, S.Hinv + lane);
+      float Gr[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) Gr[k] = S.G[k];
+      nv = 0;
+      for (int i0 = 0; i0 < P; i0 += 32) {
+        const int i = i0 + lane;
+        int v = 0;
+        if (i < P) v = place_point(Gr, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i);
+        nv += __popc(__ballot_sync(0xffffffffu, v));
+      }
+      normdp_init = 1e-10f;              // odometer.cpp:341-342: normdp = normdp_init = 1e-10
+      if (lane == 0) {
+        S.it = 0;
+        S.cont = (0 < op.maxiter) & ((1e-10f / 1e-10f) > op.normdp_ratio);
+        if (TRACE) S.lvl_cycles = (float)(clock64() - t_lv0);
+      }
+    }
+    __syncthreads();
+
+    // ---- iterations (odometer.cpp:344-419) ----------------------------------------------------------------------------
+    int it = 0;
+    while (S.cont) {
+      const long long t_it0 = TRACE ? clock64() : 0;   // instrumentation only (trace records [22], [23])
+      float2* part = s_part + (it & 1) * G_all;
+      for (int g = warp; g < G_all; g += nw) {
+        const int i = g / GPP, gp = g - i * GPP;
+        const float4 pa = s_npl[2 * i], pw = s_npl[2 * i + 1];
+        float ax = 0.0f, ay = 0.0f;                   // sums of dx*pdiff, dy*pdiff over this group
+        if (__float_as_int(pa.y)) {                   // uniform across the warp
+          const int tq = (i * 8 + gp * RQ) * 32 + lane;
+          const float* pI = Inew + (__float_as_int(pa.x) + (gp * KT) * width + lane);
+          float c_ = __ldg(pI - width), d_ = __ldg(pI - width - 1);
+#pragma unroll
+          for (int jq = 0; jq < RQ; ++jq) {
+            const float a0 = __ldg(pI), b0 = __ldg(pI - 1);
+            pI += width;
+            const float a1 = __ldg(pI), b1 = __ldg(pI - 1);
+            pI += width;
+            const float a2 = __ldg(pI), b2 = __ldg(pI - 1);
+            pI += width;
+            const float a3 = __ldg(pI), b3 = __ldg(pI - 1);
+            pI += width;
+            const float4 R = s_ref4[tq + jq * 32], GX = s_gx4[tq + jq * 32], GY = s_gy4[tq + jq * 32];
+            // util_getPatch (utilities.cpp:107) with fused multiply-adds, then pdiff = ref - new (odometer.cpp:381)
+            const float n0 = fmaf(pw.w, d_, fmaf(pw.z, c_, fmaf(pw.y, b0, pw.x * a0)));
+            const float n1 = fmaf(pw.w, b0, fmaf(pw.z, a0, fmaf(pw.y, b1, pw.x * a1)));
+            const float n2 = fmaf(pw.w, b1, fmaf(pw.z, a1, fmaf(pw.y, b2, pw.x * a2)));
+            const float n3 = fmaf(pw.w, b2, fmaf(pw.z, a2, fmaf(pw.y, b3, pw.x * a3)));
+            const float p0 = R.x - n0, p1 = R.y - n1, p2 = R.z - n2, p3 = R.w - n3;
+            ax = fmaf(GX.x, p0, ax); ay = fmaf(GY.x, p0, ay);
+            ax = fmaf(GX.y, p1, ax); ay = fmaf(GY.y, p1, ay);
+            ax = fmaf(GX.z, p2, ax); ay = fmaf(GY.z, p2, ay);
+            ax = fmaf(GX.w, p3, ax); ay = fmaf(GY.w, p3, ay);
+            c_ = a3; d_ = b3;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ax = ax + __shfl_xor_sync(0xffffffffu, ax, o);
+            ay = ay + __shfl_xor_sync(0xffffffffu, ay, o);
+          }
+        }
+        if (lane == 0) part[g] = make_float2(ax, ay);
+      }
+      const long long t_par = TRACE ? clock64() : 0;
+      __syncthreads();
+
+      // ---- serial section: one warp, every lane active, ~250 instructions --------------------------------------------
+      if (warp == swarp) {
+        const long long t_ser0 = TRACE ? clock64() : 0;
+        const unsigned FULL = 0xffffffffu;
+        const int k = lane & 7, k6 = k < 6 ? k : 0, j4 = lane >> 3;
+        // 9a. J^T r from the per-point sums: sum_k = sum_i (A_ki * ax_i + B_ki * ay_i).  Lane (k + 8j) takes the
+        //     points i = j, j+4, ...; two butterfly steps add the four point slots in a fixed order.
+        const float4 h0 = *reinterpret_cast<const float4*>(S.Hinv + 8 * k);        // row k of H^-1 (issued early)
+        const float2 h1 = *reinterpret_cast<const float2*>(S.Hinv + 8 * k + 4);
+        float bk = 0.0f;
+        if (P <= 4) {                                  // one point per lane slot: no loop
+          if (j4 < P) {
+            float2 v = part[j4 * GPP];
+#pragma unroll
+            for (int q = 1; q < GPP; ++q) {
+              const float2 u = part[j4 * GPP + q];
+              v.x = v.x + u.x;
+              v.y = v.y + u.y;
+            }
+            bk = fmaf(v.y, s_AB[j4 * 12 + 6 + k6], v.x * s_AB[j4 * 12 + k6]);
+          }
+        } else {
+#pragma unroll 1
+          for (int i = j4; i < P; i += 4) {
+            float2 v = part[i * GPP];
+#pragma unroll
+            for (int q = 1; q < GPP; ++q) {
+              const float2 u = part[i * GPP + q];
+              v.x = v.x + u.x;
+              v.y = v.y + u.y;
+            }
+            bk = bk + fmaf(v.y, s_AB[i * 12 + 6 + k6], v.x * s_AB[i * 12 + k6]);
+          }
+        }
+        bk = bk + __shfl_xor_sync(FULL, bk, 8);
+        bk = bk + __shfl_xor_sync(FULL, bk, 16);
+        // 9b. delta_p = M * J^T r: Eigen's solve (odometer.cpp:407) tabulated once per level, lane k takes row k
+        const float b0 = __shfl_sync(FULL, bk, 0), b1 = __shfl_sync(FULL, bk, 1), b2 = __shfl_sync(FULL, bk, 2);
+        const float b3 = __shfl_sync(FULL, bk, 3), b4 = __shfl_sync(FULL, bk, 4), b5 = __shfl_sync(FULL, bk, 5);
+        const float dpk = fmaf(h1.y, b5, fmaf(h1.x, b4, fmaf(h0.w, b3, fmaf(h0.z, b2, fmaf(h0.y, b1, h0.x * b0)))));
+        // 10. addpose_se3 (pose.cpp:116-129): p += delta_p, G = exp(p)
+        pk = pk + dpk;
+        const float q0 = __shfl_sync(FULL, pk, 0), q1 = __shfl_sync(FULL, pk, 1), q2 = __shfl_sync(FULL, pk, 2);
+        const float q3 = __shfl_sync(FULL, pk, 3), q4 = __shfl_sync(FULL, pk, 4), q5 = __shfl_sync(FULL, pk, 5);
+        // lpNorm<1> (odometer.cpp:412) in the reference's order ((|d0|+|d2|) + (|d1|+|d3|)) + (|d4|+|d5|)
+        float normdp = fabsf(dpk);
+        normdp = normdp + __shfl_xor_sync(FULL, normdp, 2);
+        normdp = normdp + __shfl_xor_sync(FULL, normdp, 1);
+        normdp = normdp + __shfl_xor_sync(FULL, normdp, 4);
+        if (lane < 6) S.p[lane] = pk;
+        float Gr[12];
+        Gr[3] = Gr[7] = Gr[11] = 0.0f;
+        se3_exp_regs(Gr, q0, q1, q2, q3, q4, q5, S.G, S.p);
+        if (it == 0) normdp_init = normdp;
+        const int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
+        if (lane == 0) {
+          *reinterpret_cast<float4*>(S.G) = make_float4(Gr[0], Gr[1], Gr[2], Gr[3]);
+          *reinterpret_cast<float4*>(S.G + 4) = make_float4(Gr[4], Gr[5], Gr[6], Gr[7]);
+          *reinterpret_cast<float4*>(S.G + 8) = make_float4(Gr[8], Gr[9], Gr[10], Gr[11]);
+          S.it = it + 1;
+          S.cont = cont;
+        }
+        if (TRACE) {
+          if (trace && trace_n < prm.trace_cap) {
+            float* rec = trace + (int64_t)ICT_TRACE_FLOATS * trace_n;
+            if (lane < 6) { rec[2 + lane] = bk; rec[8 + lane] = dpk; }
+            if (lane == 0) {
+              rec[0] = (float)sl;
+              rec[1] = (float)it;
+              rec[14] = normdp;
+              rec[15] = (float)nv;
+              rec[16] = 0.0f;
+              rec[20] = 0.0f;
+              rec[17] = (float)(t_ser0 - t_par);         // cycles this warp waited at the barrier for the others
+              rec[19] = S.gather_cycles;                 // cycles of this level's placement + template gather
+              rec[21] = S.lvl_cycles;                    // cycles of this level's Hessian fold + LU + inverse
+              rec[22] = (float)(clock64() - t_ser0);     // cycles of the serial section up to here
+              rec[23] = (float)(t_par - t_it0);          // cycles the serial warp spent in the pixel section
+            }
+          }
+        }
+        nvsum += nv;
+        // 7. project_pt with the new pose + new-frame placement for the next iteration (one point per lane)
+        if (cont) {
+          nv = 0;
+          for (int i0 = 0; i0 < P; i0 += 32) {
+            const int i = i0 + lane;
+            int v = 0;
+            if (i < P) v = place_point(Gr, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i);
+            nv += __popc(__ballot_sync(FULL, v));
+          }
+        }
+        if (TRACE) {
+          if (trace && trace_n < prm.trace_cap) {
+            if (lane == 0) trace[(int64_t)ICT_TRACE_FLOATS * trace_n + 18] = (float)(clock64() - t_ser0);
+            ++trace_n;
+          }
+        }
+      }
+      __syncthreads();
+      ++it;
+    }
+    // (S.it is next written by the serial warp two barriers further down, in the next level's set-up)
+    if (tid == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
+  }
+
+  if (warp == swarp && lane == 0) {
+    getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
+                prm.p_out + 6 * (int64_t)t);
+    if (prm.npixres) prm.npixres[t] = (long long)nvsum * N;
+    if (trace)
+      for (int k = trace_n; k < prm.trace_cap; ++k) {
+        float* rec = trace + (int64_t)ICT_TRACE_FLOATS * k;
+        for (int j = 0; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
+        rec[0] = -1.0f;
+      }
+  }
+}
+
+size_t v2_smem_bytes(const ict_optparam& op, int max_pts) {
+  const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
+  return sizeof(float) * (3 * P * 1024 + 72 * P);
+}
+
+template <int KT, int MINB, bool TRACE>
+static cudaError_t launch_v2_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ICT_TRACK_SMEM_LIMIT);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_track_v2<KT, MINB, TRACE><<<prm.T, 256, smem, stream>>>(prm);
+  count_launch_external();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t stream) {
+  if (prm.T <= 0) return cudaSuccess;
+  const size_t smem = v2_smem_bytes(prm.op, max_pts);
+  if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("ICT_V2_VARIANT");       // tuning knob for profiling runs only
+    variant = e ? atoi(e) : 0;
+  }
+  if (prm.trace) return launch_v2_t<16, 4, true>(prm, smem, stream);   // same arithmetic + per-iteration records
+  switch (variant) {
+    case 1: return launch_v2_t<8, 4, false>(prm, smem, stream);
+    case 3: return launch_v2_t<16, 3, false>(prm, smem, stream);
+    default: return launch_v2_t<16, 4, false>(prm, smem, stream);
+  }
+}
+
+}  // namespace ict

@@ -63,6 +63,11 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
+// K2v2 (ict_kernel_v2.cu): the production kernel for psz 32 without dopatchnorm, tree sums; launch_track routes
+// to it unless ICT_FAST_V1 is set (then k_track_fast, the previous production kernel, runs — for A/B measurements).
+size_t v2_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
 // K2p: two track slots per persistent CTA, serial steps of one slot overlapped with pixel steps of the other.
 // ticket: one device int (zeroed by the launch).  Handles psz 8/16/32 without dopatchnorm, tree sums.
 size_t pipe_smem_bytes(const ict_optparam& op, int max_pts);
