@@ -481,6 +481,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.force_general = tr->force_general;
   prm.dbg_skip_serial = getenv("ICT_DBG_SKIP_SERIAL") ? 1 : 0;
   prm.serial_warp_last = getenv("ICT_SERIAL_WARP_LAST") ? 1 : 0;
+  prm.v2_lu_setup = getenv("ICT_V2_LU") ? 1 : 0;
   const size_t smem = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode);
   // K2p (two slots per persistent CTA, ict_kernel_pipe.cu) measured 2.67e11 against 3.2e11 pixel-residuals/s for one
   // track per CTA on B200; it stays selectable for experiments and is covered by a parity test.

@@ -107,6 +107,59 @@ __device__ __forceinline__ void lu6_solve_matrix_column(const Lu6& f, int col, f
 #undef LU
 }
 
+// The same matrix M from the Hessian directly, without a factorisation: symmetric Gauss-Jordan sweeps with the pivot
+// taken as the largest remaining diagonal entry.  For a symmetric positive semi-definite matrix that is the pivot
+// Eigen's full pivoting finds (|a_ij| <= max(a_ii, a_jj)), the Schur complements that appear are the ones its
+// elimination forms, and stopping at the first pivot <= maxpivot * 6 eps is its rank rule (FullPivLU::rank with the
+// default threshold): after sweeping the index set K the K x K block holds -(H_KK)^-1, which is what the truncated
+// solve applies to b_K, and the unknowns outside K are zero.
+// Lane q < 21 holds H(i, j), i <= j, q = the position in ComputeHessian's order (row-major upper triangle).  Per
+// sweep: one integer REDUX + vote for the pivot (positive floats order like their bit patterns), one IEEE
+// reciprocal, two shuffles for a_ik and a_kj, one update — ~35 instructions, all lanes, six sweeps at most.
+__device__ __forceinline__ void sweep6_solve_matrix(float a, float* Hinv /* shared, 8 x 8, zeroed */) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int i = 0, j = 0;
+  {
+    int k = lane < 21 ? lane : 0, len = 6;
+    while (k >= len) { k -= len; --len; ++i; }
+    j = i + k;
+  }
+  // source lanes of a_ik and a_kj for k = 0..5, five bits each
+  unsigned tu = 0, tv = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int iu = min(i, k), ju = max(i, k), iv = min(j, k), jv = max(j, k);
+    tu |= (unsigned)(iu * 6 - (iu * (iu - 1)) / 2 + (ju - iu)) << (5 * k);
+    tv |= (unsigned)(iv * 6 - (iv * (iv - 1)) / 2 + (jv - iv)) << (5 * k);
+  }
+  const bool diag = (i == j) && lane < 21;
+  unsigned done = 0;                     // swept indices (uniform)
+  float maxpivot = 0.0f;
+#pragma unroll 1
+  for (int step = 0; step < 6; ++step) {
+    const unsigned bits = (diag && !((done >> i) & 1u) && a > 0.0f) ? __float_as_uint(a) : 0u;
+    const unsigned best = __reduce_max_sync(FULL, bits);
+    const float pivot = __uint_as_float(best);
+    if (step == 0) maxpivot = pivot;
+    if (!(pivot > maxpivot * (1.1920929e-07f * 6.0f))) break;   // rank reached (or H == 0)
+    const int src = __ffs(__ballot_sync(FULL, bits == best)) - 1;
+    const int k = __shfl_sync(FULL, i, src);
+    const float r = 1.0f / pivot;
+    const float u = __shfl_sync(FULL, a, (tu >> (5 * k)) & 31u);   // a_ik
+    const float v = __shfl_sync(FULL, a, (tv >> (5 * k)) & 31u);   // a_kj
+    if (i == k && j == k) a = -r;
+    else if (i == k || j == k) a = a * r;
+    else a = a - (u * r) * v;
+    done |= 1u << k;
+  }
+  if (lane < 21) {
+    const float m = (((done >> i) & 1u) && ((done >> j) & 1u)) ? -a : 0.0f;
+    Hinv[i * 8 + j] = m;
+    Hinv[j * 8 + i] = m;
+  }
+}
+
 // the reference's float exp for the two rare branches (Taylor for sigma <= 1e-4, library sincos beyond pi/4)
 static __device__ __noinline__ void se3_exp_rare(float* G, const float* p) { se3_exp<float>(G, p); }
 
@@ -331,7 +384,7 @@ __global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
     }
     __syncthreads();
 
-    // ---- 6b. Hessian from the per-point sums, LU factorisation, first placement -----------------------------------
+    // ---- 6b. Hessian from the per-point sums, the level's solve matrix, first placement -----------------------------------
     if (warp == swarp) {
       const long long t_lv0 = TRACE ? clock64() : 0;
       if (TRACE && lane == 0) S.gather_cycles = (float)(t_lv0 - t_g0);
@@ -357,12 +410,15 @@ __global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
         }
         S.Hsum[lane] = h;
       }
-      __syncwarp();
-      lu6_factor_warp(S.Hsum, S.f);      // all 32 lanes; same elimination (and rank decision) as Eigen's fullPivLu
       S.Hinv[lane] = 0.0f;
       S.Hinv[32 + lane] = 0.0f;
       __syncwarp();
-      if (lane < 6) lu6_solve_matrix_column(S.f, lane, S.Hinv + lane);
+      if (prm.v2_lu_setup) {             // A/B knob (ICT_V2_LU): Eigen's elimination itself, then M column by column
+        lu6_factor_warp(S.Hsum, S.f);
+        if (lane < 6) lu6_solve_matrix_column(S.f, lane, S.Hinv + lane);
+      } else {
+        sweep6_solve_matrix(lane < 21 ? S.Hsum[lane] : 0.0f, S.Hinv);
+      }
       float Gr[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) Gr[k] = S.G[k];
@@ -559,8 +615,10 @@ static cudaError_t launch_v2_t(const TrackParams& prm, size_t smem, cudaStream_t
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
+    const char* co = getenv("ICT_V2_CARVEOUT");      // profiling knob: shared-memory carve-out in percent
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               co ? atoi(co) : 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

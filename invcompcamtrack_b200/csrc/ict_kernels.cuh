@@ -41,6 +41,7 @@ struct TrackParams {
   int t0;                          // first track of this launch (index into the per-track arrays)
   int serial_warp_last;            // profiling knob: run the serial sections on the CTA's last warp instead of warp 0
   int dbg_skip_serial;             // profiling experiment: skip solve/update (results meaningless)
+  int v2_lu_setup;                 // K2v2 A/B knob: per-level solve matrix from the warp LU instead of the sweeps
   int force_general;               // 1: always use the general kernel k_track (tests compare the two)
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
                                    //    with the oracle's default model of the reference, ~3x slower)
