@@ -219,6 +219,29 @@ __device__ __forceinline__ void se3_exp_regs(float* G, float p0, float p1, float
   G[11] = (tmp4 - tmp3) * p0 + (tmp5 + tmp6) * p1 + (1 - (ra1 + ra2) * sc) * p2;
 }
 
+// util_getPatch_grad (utilities.cpp:160-185) for KT consecutive rows of one patch column: p points at the row ABOVE
+// the first one (the bilinear sample of row r reads rows r and r-1, columns c and c-1); unfused, in the reference's
+// order ((w0*a + w1*b) + w2*c) + w3*d.  Writes KT/4 float4 row-quads at dst, dst + 32, ...
+template <int KT>
+__device__ __forceinline__ void gather_plane(const float* __restrict__ p, int width, const float4 w, float4* dst) {
+  float a[KT + 1], b[KT + 1];
+#pragma unroll
+  for (int j = 0; j <= KT; ++j) {
+    a[j] = __ldg(p + j * width);
+    b[j] = __ldg(p + j * width - 1);
+  }
+#pragma unroll
+  for (int jq = 0; jq < KT / 4; ++jq) {
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = 4 * jq + j + 1;
+      r[j] = ((w.x * a[row] + w.y * b[row]) + w.z * a[row - 1]) + w.w * b[row - 1];
+    }
+    dst[jq * 32] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 template <int KT, int MINB, bool TRACE>
 __global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
   constexpr int N = 1024;                 // pixels per patch (psz 32)
@@ -334,45 +357,23 @@ __global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
       const int i = g / GPP, gp = g - i * GPP;
       const float4 pa = s_rpl[2 * i], pw = s_rpl[2 * i + 1];
       const int tq = (i * 8 + gp * RQ) * 32 + lane;
-      float sxx = 0.0f, sxy = 0.0f, syy = 0.0f;
       if (__float_as_int(pa.y)) {
-        const int o0 = __float_as_int(pa.x) + (gp * KT) * width + lane;
-        const float* pI = Iref + o0;
-        const float* pX = Dxr + o0;
-        const float* pY = Dyr + o0;
-        float ci = __ldg(pI - width), di = __ldg(pI - width - 1);
-        float cxx = __ldg(pX - width), dxx = __ldg(pX - width - 1);
-        float cyy = __ldg(pY - width), dyy = __ldg(pY - width - 1);
+        // one plane at a time, all 2 * (KT + 1) loads of the plane issued before the first use: the gather is bound by
+        // the L2 round trip, not by arithmetic, so the number of loads in flight per warp is what matters
+        const int o0 = __float_as_int(pa.x) + (gp * KT - 1) * width + lane;
+        gather_plane<KT>(Iref + o0, width, pw, s_ref4 + tq);
+        gather_plane<KT>(Dxr + o0, width, pw, s_gx4 + tq);
+        gather_plane<KT>(Dyr + o0, width, pw, s_gy4 + tq);
+      }
+      // (a point out of the reference image keeps the previous level's template)
+      float sxx = 0.0f, sxy = 0.0f, syy = 0.0f;
 #pragma unroll
-        for (int jq = 0; jq < RQ; ++jq) {
-          float r[4], gx[4], gy[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ai = __ldg(pI), bi = __ldg(pI - 1);
-            const float ax_ = __ldg(pX), bx_ = __ldg(pX - 1);
-            const float ay_ = __ldg(pY), by_ = __ldg(pY - 1);
-            pI += width; pX += width; pY += width;
-            r[j] = ((pw.x * ai + pw.y * bi) + pw.z * ci) + pw.w * di;
-            gx[j] = ((pw.x * ax_ + pw.y * bx_) + pw.z * cxx) + pw.w * dxx;
-            gy[j] = ((pw.x * ay_ + pw.y * by_) + pw.z * cyy) + pw.w * dyy;
-            ci = ai; di = bi; cxx = ax_; dxx = bx_; cyy = ay_; dyy = by_;
-            sxx = fmaf(gx[j], gx[j], sxx);
-            sxy = fmaf(gx[j], gy[j], sxy);
-            syy = fmaf(gy[j], gy[j], syy);
-          }
-          s_ref4[tq + jq * 32] = make_float4(r[0], r[1], r[2], r[3]);
-          s_gx4[tq + jq * 32] = make_float4(gx[0], gx[1], gx[2], gx[3]);
-          s_gy4[tq + jq * 32] = make_float4(gy[0], gy[1], gy[2], gy[3]);
-        }
-      } else {                           // out of the reference image: the previous level's template stays
-#pragma unroll
-        for (int jq = 0; jq < RQ; ++jq) {
-          const float4 gx = s_gx4[tq + jq * 32], gy = s_gy4[tq + jq * 32];
-          sxx = fmaf(gx.x, gx.x, sxx); sxy = fmaf(gx.x, gy.x, sxy); syy = fmaf(gy.x, gy.x, syy);
-          sxx = fmaf(gx.y, gx.y, sxx); sxy = fmaf(gx.y, gy.y, sxy); syy = fmaf(gy.y, gy.y, syy);
-          sxx = fmaf(gx.z, gx.z, sxx); sxy = fmaf(gx.z, gy.z, sxy); syy = fmaf(gy.z, gy.z, syy);
-          sxx = fmaf(gx.w, gx.w, sxx); sxy = fmaf(gx.w, gy.w, sxy); syy = fmaf(gy.w, gy.w, syy);
-        }
+      for (int jq = 0; jq < RQ; ++jq) {  // this lane's own writes: no barrier needed
+        const float4 gx = s_gx4[tq + jq * 32], gy = s_gy4[tq + jq * 32];
+        sxx = fmaf(gx.x, gx.x, sxx); sxy = fmaf(gx.x, gy.x, sxy); syy = fmaf(gy.x, gy.x, syy);
+        sxx = fmaf(gx.y, gx.y, sxx); sxy = fmaf(gx.y, gy.y, sxy); syy = fmaf(gy.y, gy.y, syy);
+        sxx = fmaf(gx.z, gx.z, sxx); sxy = fmaf(gx.z, gy.z, sxy); syy = fmaf(gy.z, gy.z, syy);
+        sxx = fmaf(gx.w, gx.w, sxx); sxy = fmaf(gx.w, gy.w, sxy); syy = fmaf(gy.w, gy.w, syy);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
