@@ -100,7 +100,7 @@ def make_workload(rank, S, T, P, psz, w, h, lv_f, ntex):
     return dict(frames=frames, pts=pts, pt_off=pt_off, ref=ref, new=new, p_gt=p_gt, fc=fc, cc=cc, wh=wh)
 
 
-def cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, threads, use_ref):
+def cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, threads, use_ref, spread=False):
     """Times the CPU implementation (oracle port or oracle/_ref) on `seqs` sequences of the same workload."""
     from oracle import oracle as O
     orc = O.OracleLib()
@@ -126,8 +126,19 @@ def cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, threads, use_ref):
         orc.track_batch(*args, nthreads=threads)
         dt = time.perf_counter() - t0
         kind = "port"
+    alt = None
+    if spread:
+        # the same sample with the reference's sums in the other packet order its unpinned Eigen could have used
+        # (AVX instead of SSE packets): how far the REFERENCE moves from itself when only that order changes
+        orc.set_sum_mode(1)
+        alt = orc.track_batch(*args, nthreads=threads)
+        orc.set_sum_mode(0)
     return dict(value=npix / dt, tracks_per_s=n / dt, seconds=dt, kind=kind, npix=npix, tracks=n,
-                pyramid_ms_per_frame=1e3 * t_pyr / (2 * seqs), p_out=counted["p_out"], iters=counted["iters"])
+                pyramid_ms_per_frame=1e3 * t_pyr / (2 * seqs), p_out=counted["p_out"], iters=counted["iters"],
+                alt=alt)
+
+
+KERNEL_NAME = "k_track_v2<16,4,false>"   # the production kernel for psz 32 (ict_kernel_v2.cu)
 
 
 def main():
@@ -145,6 +156,8 @@ def main():
     ap.add_argument("--cpu-seqs", type=int, default=env_int("ICT_BENCH_CPU_SEQS", 8), help="sequences in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=env_int("ICT_BENCH_E2E_CHUNKS", 4),
+                    help="chunks of sequences the host-buffer path pipelines over two streams")
     ap.add_argument("--maxiter", type=int, default=10)
     ap.add_argument("--ratio", type=float, default=0.01, help="normdp_ratio")
     ap.add_argument("--textures", type=int, default=4, help="distinct textures shared by the sequences (setup time)")
@@ -275,28 +288,34 @@ def main():
         lib = ict.lib()
         v = C.c_void_p
 
-        # The batch goes through the C ABI in chunks of sequences on two streams, one tracker per chunk, so that the
-        # H2D copy of one chunk's frames overlaps the tracking of the previous chunk (ict_*_stream entry points).
-        nchunk = min(4, S)
+        # The batch goes through the C ABI in chunks of sequences on ONE stream, one tracker per chunk: the *_stream
+        # entry points run their host->device copies on internal copy lanes, so the copy of chunk c+1 overlaps the
+        # tracking of chunk c while all kernels stay in call order on this stream (two caller streams made the
+        # pyramid kernel of the next chunk run inside the tracking kernel at a fraction of its occupancy).
+        nchunk = max(1, min(a.e2e_chunks, S))
         bounds = [(c * S) // nchunk for c in range(nchunk + 1)]
-        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        streams = [torch.cuda.Stream()]
         chunk_trackers = [ict.Tracker(op, wl["fc"], wl["cc"], wl["wh"]) for _ in range(nchunk)]
+        # every host buffer the ABI reads asynchronously is pinned (a pageable source makes cudaMemcpyAsync wait for
+        # the stream and serialises the pipeline)
+        h_ref = torch.from_numpy(wl["ref"]).pin_memory()
+        h_new = torch.from_numpy(wl["new"]).pin_memory()
         chunk_off = []
         for c in range(nchunk):
             t0_, t1_ = bounds[c] * T, bounds[c + 1] * T
-            chunk_off.append(np.ascontiguousarray(wl["pt_off"][t0_:t1_ + 1] - wl["pt_off"][t0_]))
+            chunk_off.append(torch.from_numpy(np.ascontiguousarray(wl["pt_off"][t0_:t1_ + 1] - wl["pt_off"][t0_])).pin_memory())
 
         def step_host():
             for c in range(nchunk):
-                st = v(streams[c % 2].cuda_stream)
+                st = v(streams[0].cuda_stream)
                 s0, s1 = bounds[c], bounds[c + 1]
                 t0_, t1_ = s0 * T, s1 * T
                 rc = lib.ict_frames_upload_u8_stream(frames.h_, 2 * s0, 2 * (s1 - s0),
                                                      v(h_frames.data_ptr() + 2 * s0 * w * h), st)
-                rc |= lib.ict_tracker_set_points_stream(chunk_trackers[c].h_, t1_ - t0_, v(chunk_off[c].ctypes.data),
+                rc |= lib.ict_tracker_set_points_stream(chunk_trackers[c].h_, t1_ - t0_, v(chunk_off[c].data_ptr()),
                                                         v(h_pts.data_ptr() + 8 * 3 * int(wl["pt_off"][t0_])), st)
-                rc |= lib.ict_track_batch_stream(chunk_trackers[c].h_, frames.h_, v(wl["ref"].ctypes.data + 4 * t0_),
-                                                 v(wl["new"].ctypes.data + 4 * t0_), v(h_pin.data_ptr() + 48 * t0_),
+                rc |= lib.ict_track_batch_stream(chunk_trackers[c].h_, frames.h_, v(h_ref.data_ptr() + 4 * t0_),
+                                                 v(h_new.data_ptr() + 4 * t0_), v(h_pin.data_ptr() + 48 * t0_),
                                                  v(h_pout.data_ptr() + 48 * t0_), v(h_iters.data_ptr() + 4 * L * t0_),
                                                  v(h_npix.data_ptr() + 8 * t0_), st)
                 if rc:
@@ -374,7 +393,7 @@ def main():
                 "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "pixel_residuals_per_step_per_gpu": npix_step, "gn_iterations_per_track": iters_mean,
-                "roofline": {"bound": "hbm", "kernel": "k_track<32,false>", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": KERNEL_NAME if psz == 32 else "k_track_fast<%d>" % psz, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_pixel_residual": BYTES_PER_PIXRES,
                              "kernel_ms_per_launch": ms_kernel,
@@ -387,18 +406,54 @@ def main():
                            "tracks_per_s": NT * world * a.steps / (ms_e2e_all * 1e-3)}
         if world == 1 and not a.no_cpu:
             seqs = max(1, min(a.cpu_seqs, S))
-            cb = cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, cores, use_ref=False)
+            cb = cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, cores, use_ref=False, spread=True)
             # parity spot-check of the benchmark's own result against the oracle on the sampled tracks
-            g = d_pout[:cb["tracks"]].cpu().numpy()
-            same = float((d_iters[:cb["tracks"]].cpu().numpy() == cb["iters"]).mean())
+            n = cb["tracks"]
+            g = d_pout[:n].cpu().numpy()
+            same = float((d_iters[:n].cpu().numpy() == cb["iters"]).mean())
+            dg = np.abs(g - cb["p_out"]).max(axis=1)
+            da = np.abs(cb["alt"]["p_out"] - cb["p_out"]).max(axis=1)
+            same_alt = float((cb["alt"]["iters"] == cb["iters"]).mean())
+            # the reference-order kernel (ict_tracker_set_sum_order 1) on the same tracks: must EQUAL the oracle
+            tr_x = ict.Tracker(op, wl["fc"], wl["cc"], wl["wh"])
+            tr_x.set_sum_order(1)
+            x_pout = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+            x_iters = torch.zeros(n, L, dtype=torch.int32, device=dev)
+            x_npix = torch.zeros(n, dtype=torch.int64, device=dev)
+            tr_x.set_points_dev(n, d_off.data_ptr(), d_pts.data_ptr(), n * P, P, stream=stream)
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(2):
+                x0.record()
+                tr_x.track_batch_dev(frames, d_ref.data_ptr(), d_new.data_ptr(), d_pin.data_ptr(), x_pout.data_ptr(),
+                                     iters_ptr=x_iters.data_ptr(), npix_ptr=x_npix.data_ptr(), stream=stream)
+                x1.record()
+                torch.cuda.synchronize()
+            x_ms = x0.elapsed_time(x1)
+            exact = bool(np.array_equal(x_pout.cpu().numpy(), cb["p_out"]) and
+                         np.array_equal(x_iters.cpu().numpy(), cb["iters"]))
+            tr_x.close()
             line["cpu_baseline"] = {
                 "value": cb["value"], "unit": "pixel-residuals/s", "cores": cores, "kind": cb["kind"],
                 "tracks_per_s": cb["tracks_per_s"],
                 "sample": "%d of the %d sequences (%d tracks), %.1f s, oracle port (plain C, -O3 -msse4 -mavx), OpenMP "
                           "over tracks; span Set3Dpoints->SetPose->TrackPose; pyramids %.1f ms/frame on 1 thread extra"
                           % (seqs, S, cb["tracks"], cb["seconds"], cb["pyramid_ms_per_frame"]),
-                "parity_vs_gpu": {"max_abs_pose_diff": float(np.abs(g - cb["p_out"]).max()),
-                                  "frac_identical_iteration_counts": same}}
+                "parity_vs_gpu": {
+                    "note": "4-point tracks are ill-conditioned: the reference itself moves this much when only the "
+                            "order of its own fp32 sums changes (reference_self_spread = oracle with SSE-packet vs "
+                            "AVX-packet Eigen sums); the reference-order kernel reproduces the oracle exactly",
+                    "production_kernel": {"frac_identical_iteration_counts": same,
+                                          "median_abs_pose_diff": float(np.median(dg)),
+                                          "p99_abs_pose_diff": float(np.percentile(dg, 99)),
+                                          "max_abs_pose_diff": float(dg.max())},
+                    "reference_self_spread": {"frac_identical_iteration_counts": same_alt,
+                                              "median_abs_pose_diff": float(np.median(da)),
+                                              "p99_abs_pose_diff": float(np.percentile(da, 99)),
+                                              "max_abs_pose_diff": float(da.max())},
+                    "reference_order_kernel": {"bit_identical_poses_and_iteration_counts": exact,
+                                               "tracks": int(n), "ms": x_ms,
+                                               "value": float(x_npix.sum().item()) / (x_ms * 1e-3),
+                                               "unit": "pixel-residuals/s"}}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -55,6 +55,49 @@ struct DevBuf {
   template <typename T> T* as() const { return (T*)p; }
 };
 
+// Internal copy lane of the *_stream entry points.  Host->device copies of a call run on the object's own stream and
+// the caller's stream waits for them by event, so the copy of call k+1 overlaps whatever the caller's stream is
+// still executing for call k, while every KERNEL stays on the caller's one stream in call order.  (Kernels of two
+// calls on two caller streams do overlap, but badly: the small pyramid CTAs of the next chunk take the slots that
+// tracking CTAs free one by one and run at a fraction of their normal occupancy — measured +0.7 ms per 6.2 ms chunk,
+// profiles/tools/e2e_timeline.py.)  `consumed` is recorded on the caller's stream after the last kernel that reads the
+// copy's destination; the lane waits for it before overwriting the destination in a later call.
+struct CopyLane {
+  cudaStream_t s = nullptr;
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+  bool have_consumed = false;
+  cudaError_t begin() {                     // call before the copies of one API call
+    cudaError_t e = cudaSuccess;
+    if (!s) {
+      e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&consumed, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    if (have_consumed) e = cudaStreamWaitEvent(s, consumed, 0);
+    return e;
+  }
+  cudaError_t publish(cudaStream_t user) {  // after the copies: the caller's stream sees them
+    cudaError_t e = cudaEventRecord(copied, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, copied, 0);
+    return e;
+  }
+  cudaError_t done(cudaStream_t user) {     // after the last kernel that reads the copied data
+    cudaError_t e = cudaEventRecord(consumed, user);
+    have_consumed = e == cudaSuccess;
+    return e;
+  }
+  void release() {
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaEventDestroy(copied);
+      cudaEventDestroy(consumed);
+      cudaStreamDestroy(s);
+      s = nullptr;
+    }
+  }
+};
+
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------------
@@ -154,6 +197,7 @@ struct ict_frames {
   float *I, *dx, *dy;
   FrameDesc* desc;
   DevBuf stage;
+  CopyLane lane;
   bool view;
 };
 
@@ -202,6 +246,7 @@ void ict_frames_destroy(ict_frames* fs) {
   if (fs->dy) cudaFree(fs->dy);
   if (fs->desc) cudaFree(fs->desc);
   fs->stage.release();
+  fs->lane.release();
   delete fs;
 }
 
@@ -293,8 +338,13 @@ int ict_frames_upload_u8_stream(ict_frames* fs, int first, int count, const unsi
     CU(fs->stage.reserve(per * fs->nframes));
   }
   unsigned char* dst = fs->stage.as<unsigned char>() + per * first;
-  CU(cudaMemcpyAsync(dst, imgs, per * count, cudaMemcpyHostToDevice, st));
-  return frames_build(fs, first, count, nullptr, dst, st);
+  CU(fs->lane.begin());
+  CU(cudaMemcpyAsync(dst, imgs, per * count, cudaMemcpyHostToDevice, fs->lane.s));
+  CU(fs->lane.publish(st));
+  const int rc = frames_build(fs, first, count, nullptr, dst, st);
+  if (rc) return rc;
+  CU(fs->lane.done(st));
+  return ICT_OK;
 }
 
 int ict_frames_download(ict_frames* fs, int frame, float* out_I, float* out_dx, float* out_dy) {
@@ -332,6 +382,8 @@ struct ict_tracker {
   int sum_mode = 0;
   int force_general = 0;
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, ticket;
+  CopyLane lane;      // points (ict_tracker_set_points_stream)
+  CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
 };
 
 ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2]) {
@@ -354,6 +406,8 @@ void ict_tracker_destroy(ict_tracker* tr) {
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
                  &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->ticket};
   for (DevBuf* x : b) x->release();
+  tr->lane.release();
+  tr->lane_in.release();
   delete tr;
 }
 
@@ -417,10 +471,13 @@ int ict_tracker_set_points_stream(ict_tracker* tr, int T, const int64_t* pt_off,
   }
   if (tracker_reserve(tr, T, total)) return ICT_ERR_CUDA;
   CU(tr->pts.reserve(sizeof(double) * 3 * (size_t)(total ? total : 1)));
-  CU(cudaMemcpyAsync(tr->pt_off.p, pt_off, sizeof(int64_t) * (size_t)(T + 1), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(tr->pts.p, pts, sizeof(double) * 3 * (size_t)total, cudaMemcpyHostToDevice, st));
+  CU(tr->lane.begin());
+  CU(cudaMemcpyAsync(tr->pt_off.p, pt_off, sizeof(int64_t) * (size_t)(T + 1), cudaMemcpyHostToDevice, tr->lane.s));
+  CU(cudaMemcpyAsync(tr->pts.p, pts, sizeof(double) * 3 * (size_t)total, cudaMemcpyHostToDevice, tr->lane.s));
+  CU(tr->lane.publish(st));
   CU(launch_set_points(T, tr->pt_off.as<int64_t>(), tr->pts.as<double>(), nullptr, tr->pt3d.as<float>(),
                        tr->norm.as<double>(), tr->op.donorm, tr->op.maxpttrack, max_pts, st));
+  CU(tr->lane.done(st));   // pt_off stays in use by later tracking calls: ict_track_batch_stream records again
   tr->T = T;
   tr->total = total;
   tr->max_pts = max_pts;
@@ -575,12 +632,16 @@ int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref
   CU(tr->p_out.reserve(sizeof(double) * 6 * (size_t)T));
   CU(tr->iters.reserve(sizeof(int) * (size_t)T * L));
   CU(tr->npix.reserve(sizeof(long long) * (size_t)T));
-  CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, st));
+  CU(tr->lane_in.begin());
+  CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, tr->lane_in.s));
+  CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, tr->lane_in.s));
+  CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, tr->lane_in.s));
+  CU(tr->lane_in.publish(st));
   const int rc = run_tracks(tr, fs, tr->rf.as<int>(), tr->nf.as<int>(), -1, -1, tr->p_in.as<double>(),
                             tr->p_out.as<double>(), tr->iters.as<int>(), nullptr, 0, tr->npix.as<long long>(), st);
   if (rc) return rc;
+  CU(tr->lane.done(st));
+  CU(tr->lane_in.done(st));
   CU(cudaMemcpyAsync(p_out, tr->p_out.p, sizeof(double) * 6 * (size_t)T, cudaMemcpyDeviceToHost, st));
   if (iters) CU(cudaMemcpyAsync(iters, tr->iters.p, sizeof(int) * (size_t)T * L, cudaMemcpyDeviceToHost, st));
   if (npixres) CU(cudaMemcpyAsync(npixres, tr->npix.p, sizeof(long long) * (size_t)T, cudaMemcpyDeviceToHost, st));
