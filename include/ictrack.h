@@ -167,9 +167,13 @@ int ict_tracker_get_2dpoints(ict_tracker* tr, float* out);
 
 /* ---- stream-ordered host-buffer variants ------------------------------------------------------------------------
  * Same work as ict_frames_upload_u8 / ict_tracker_set_points / ict_track_batch, enqueued on the caller's
- * cudaStream_t without a final synchronisation, so that the H2D copies of one chunk of a batch overlap the tracking
- * of another (use one tracker per chunk; host buffers should be pinned and must stay valid until the stream has
- * been synchronised; outputs are valid after that).  No trace, no in-place centring of the caller's points. */
+ * cudaStream_t without a final synchronisation.  Kernels and device->host copies run on that stream in call order;
+ * the host->device copies of a call run on an internal copy lane of the object (its own stream; the caller's
+ * stream waits for it by event, and the lane waits for the last kernel that read the copy's destination), so with
+ * ONE caller stream the copies of the next chunk of a batch overlap the tracking of the current one.  Use one
+ * tracker per chunk in flight and one caller stream per frame store; host buffers must be pinned (a pageable
+ * source makes cudaMemcpyAsync wait for the stream) and stay valid and unmodified until the caller's stream has
+ * been synchronised; outputs are valid after that.  No trace, no in-place centring of the caller's points. */
 int ict_frames_upload_u8_stream(ict_frames* fs, int first, int count, const unsigned char* imgs, void* stream);
 int ict_tracker_set_points_stream(ict_tracker* tr, int T, const int64_t* pt_off, const double* pts, void* stream);
 int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref_frame, const int* new_frame,
