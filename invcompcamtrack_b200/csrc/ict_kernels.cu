@@ -1247,6 +1247,9 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
       default: return launch_track_fast_t<32>(prm, fsm, nt, stream);
     }
   }
+  if (mode == 2 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_EXACT_V1") &&
+      kx_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
+    return launch_track_x(prm, max_pts, stream);       // K2x: reference-order sums, producer/chain warps
   const int ntx = (mode & 2) && nt < 192 ? 192 : nt;   // the reference-order Hessian needs 21*8 = 168 threads
   switch (prm.op.psz) {
     case 8: return launch_track_p<8>(prm, smem, ntx, mode, stream);

@@ -69,6 +69,12 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
 size_t v2_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
+// K2x (ict_kernel_x.cu): reference-order (Eigen packet) sums for psz 32 without dopatchnorm — bit-identical to the
+// oracle like k_track<32,2>, with producer warps and one chain warp; launch_track routes sum_mode 1 to it unless
+// ICT_EXACT_V1 is set.
+size_t kx_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track_x(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
 // K2p: two track slots per persistent CTA, serial steps of one slot overlapped with pixel steps of the other.
 // ticket: one device int (zeroed by the launch).  Handles psz 8/16/32 without dopatchnorm, tree sums.
 size_t pipe_smem_bytes(const ict_optparam& op, int max_pts);
