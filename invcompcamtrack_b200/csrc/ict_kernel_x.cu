@@ -123,6 +123,47 @@ __device__ __forceinline__ float kx_finish(float s) {
   return t + __shfl_down_sync(FULL, t, 1);
 }
 
+// FullPivLU::solve (odometer.cpp:514) as straight-line code for any rank: lu6_solve of ict_device.cuh (c = P b,
+// unit-lower forward substitution over all six rows, upper backward substitution on the leading rank x rank block
+// with true divisions, zeros beyond the rank, x = Q c) with the permutations folded into the index tables and the
+// rank test as predicates — the same operations in the same order, hence the same bits; about 100 instructions
+// instead of the loops over run-time bounds and the local-memory array of the generic routine (37 % of the 4-point
+// benchmark tracks' level Hessians are rank-deficient by Eigen's threshold, so that path is not rare).
+__device__ __forceinline__ void lu6_solve_exact(const Lu6& f, const float* b, float* x) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  const int rank = f.rank;
+  float c0 = b[f.pr[0]], c1 = b[f.pr[1]], c2 = b[f.pr[2]], c3 = b[f.pr[3]], c4 = b[f.pr[4]], c5 = b[f.pr[5]];
+  if (rank == 0) c0 = c1 = c2 = c3 = c4 = c5 = 0.0f;
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  if (rank > 5) {
+    c5 = c5 / LU(5, 5);
+    c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  } else c5 = 0.0f;
+  if (rank > 4) {
+    c4 = c4 / LU(4, 4);
+    c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  } else c4 = 0.0f;
+  if (rank > 3) {
+    c3 = c3 / LU(3, 3);
+    c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  } else c3 = 0.0f;
+  if (rank > 2) {
+    c2 = c2 / LU(2, 2);
+    c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  } else c2 = 0.0f;
+  if (rank > 1) {
+    c1 = c1 / LU(1, 1);
+    c0 = c0 - c1 * LU(0, 1);
+  } else c1 = 0.0f;
+  c0 = rank > 0 ? c0 / LU(0, 0) : 0.0f;
+  x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
+#undef LU
+}
+
 __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
   constexpr int N = 1024;
   extern __shared__ __align__(16) float smem[];
@@ -299,24 +340,39 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     while (S.cont) {
       float sx = 0.0f, sy = 0.0f;
       const int rounds = (NTILE + KX_PROD - 1) / KX_PROD;
+      // producer state: the new-frame rows of the tile of the coming round, fetched one round ahead so that the L2
+      // round trip is covered by the previous round's arithmetic and barrier
+      float la[5], lb[5];
+      float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool lvis = false;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) la[r] = lb[r] = 0.0f;
+      auto fetch = [&](int tl) {
+        const int i = tl >> 3, rq = tl & 7;
+        const float4 pa = s_npl[2 * i];
+        lw = s_npl[2 * i + 1];
+        lvis = __float_as_int(pa.y) != 0;
+        if (lvis) {
+          const float* pI = Inew + (__float_as_int(pa.x) + (rq * 4 - 1) * width + lane);
+#pragma unroll
+          for (int r = 0; r < 5; ++r) { la[r] = __ldg(pI + r * width); lb[r] = __ldg(pI + r * width - 1); }
+        }
+      };
+      if (!chainw && warp < NTILE) fetch(warp);
       for (int j = 0; j <= rounds; ++j) {
         if (!chainw) {
           const int tl = j * KX_PROD + warp;
           if (j < rounds && tl < NTILE) {
-            const int i = tl >> 3, rq = tl & 7;
-            const float4 pa = s_npl[2 * i], pw = s_npl[2 * i + 1];
-            const bool vis = __float_as_int(pa.y) != 0;
+            const int i = tl >> 3;
             float4 pn4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool vis = lvis;
             if (vis) {                   // util_getPatch (utilities.cpp:55-113), unfused, reference order
-              const float* pI = Inew + (__float_as_int(pa.x) + (rq * 4 - 1) * width + lane);
-              float a[5], b[5];
-#pragma unroll
-              for (int r = 0; r < 5; ++r) { a[r] = __ldg(pI + r * width); b[r] = __ldg(pI + r * width - 1); }
-              pn4.x = ((pw.x * a[1] + pw.y * b[1]) + pw.z * a[0]) + pw.w * b[0];
-              pn4.y = ((pw.x * a[2] + pw.y * b[2]) + pw.z * a[1]) + pw.w * b[1];
-              pn4.z = ((pw.x * a[3] + pw.y * b[3]) + pw.z * a[2]) + pw.w * b[2];
-              pn4.w = ((pw.x * a[4] + pw.y * b[4]) + pw.z * a[3]) + pw.w * b[3];
+              pn4.x = ((lw.x * la[1] + lw.y * lb[1]) + lw.z * la[0]) + lw.w * lb[0];
+              pn4.y = ((lw.x * la[2] + lw.y * lb[2]) + lw.z * la[1]) + lw.w * lb[1];
+              pn4.z = ((lw.x * la[3] + lw.y * lb[3]) + lw.z * la[2]) + lw.w * lb[2];
+              pn4.w = ((lw.x * la[4] + lw.y * lb[4]) + lw.z * la[3]) + lw.w * lb[3];
             }
+            if (j + 1 < rounds && tl + KX_PROD < NTILE) fetch(tl + KX_PROD);
             const float4 R = s_ref4[tl * 32 + lane], GX = s_gx4[tl * 32 + lane], GY = s_gy4[tl * 32 + lane];
             float ab[12];
 #pragma unroll
@@ -344,8 +400,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
           float sumsd[6], dp[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) sumsd[k] = S.sum[k];
-          if (S.f.rank == 6) lu6_solve_full(S.f, S.sum, S.dp);   // 9b. odometer.cpp:407, Eigen's substitution order
-          else lu6_solve(S.f, S.sum, S.dp);
+          lu6_solve_exact(S.f, S.sum, S.dp);                     // 9b. odometer.cpp:407, Eigen's substitution order
           float pr[6], Gr[12];
 #pragma unroll
           for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; pr[k] = S.p[k] + dp[k]; S.p[k] = pr[k]; }   // 10. addpose_se3
