@@ -16,8 +16,12 @@
 //   * one CHAIN warp owns the 48 chains of the six sums (lane l: chain (k = l/8, c = l%8) and, for l < 16, chain
 //     (k = 4 + l/8, c)); per tile it reads its four columns of the four rows (4 x LDS.128 per chain) and performs
 //     the 16 additions in the reference's order;
-//   * rounds are separated by CTA barriers: in round j the producers fill half j&1 of the ring with tiles 7j..7j+6
-//     while the chain warp consumes tiles 7(j-1).. of the other half.
+//   * work proceeds in rounds of seven tiles (producer w makes tile 7j + w of round j) over a two-half staging ring;
+//     the halves are handed over with shared-memory barriers (mbarrier: `full[h]` completes when all producers have
+//     written their tile of the round, `empty[h]` when the chain warp has read the half), so the producers run one
+//     round ahead of the chain warp and nobody waits at a CTA barrier inside a sum; one CTA barrier per iteration
+//     remains (the next iteration needs the new pose).  Handing over single tiles instead was slower: every
+//     mbarrier wait costs the chain warp ~90 cycles of issue stall, 32 times per sum.
 // The chain warp then combines the chains like Eigen's redux, solves with Eigen's elimination (lu6_* of
 // ict_device.cuh), updates the pose with the reference's exp (double sqrt/sin/cos, utilities.h:84-145) and places
 // the points for the next iteration.  Template layout, gather and placement are those of K2v2 (ict_kernel_v2.cuh),
@@ -33,7 +37,30 @@ void count_launch_external();
 #define KX_PROD 7                       /* producer warps; warp KX_PROD is the chain warp */
 #define KX_TILE_F4 (6 * 32)             /* float4 per staged tile: six quantities x 32 columns (x 4 rows) */
 
+// ---- shared-memory barriers (mbarrier) for the producer -> chain hand-off of ring slots ---------------------------------
+__device__ __forceinline__ unsigned kx_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kx_saddr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {   // release at CTA scope
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kx_saddr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {   // acquire at CTA scope
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "KX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra KX_DONE;\n"
+      "bra KX_WAIT;\n"
+      "KX_DONE:\n"
+      "}\n" ::"r"(kx_saddr(b)), "r"(parity)
+      : "memory");
+}
+
 struct __align__(16) KxShared {
+  unsigned long long full[2];             // ring half written: all lanes of all producer warps arrive
+  unsigned long long empty[2];            // ring half read: the 32 chain lanes arrive
   float G[12];
   float p[8];
   float sum[8];
@@ -213,6 +240,10 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     }
   }
   if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
+  if (tid >= 32 && tid < 34) {
+    mbar_init(&S.full[tid - 32], 32 * KX_PROD);
+    mbar_init(&S.empty[tid - 32], 32);
+  }
   __syncthreads();
   for (int i = tid; i < P; i += nt) {   // project_pt_save_rotated, pose.cpp:400-488
     const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
@@ -234,6 +265,8 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
   int trace_n = 0;
   float normdp_init = 1e-10f;
   int nv = 0, nvsum = 0;          // chain warp only
+  int ground = 0;                 // rounds done so far, counted alike by every warp: half = ground & 1, use = ground >> 1
+  const int ROUNDS = (NTILE + KX_PROD - 1) / KX_PROD;
 
   for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
     const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
@@ -279,18 +312,18 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     // ---- 6. Hessian: 21 reference-order sums in four passes of six (odometer.cpp:428-472) --------------------------
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
-      float sx = 0.0f, sy = 0.0f;
-      const int rounds = (NTILE + KX_PROD - 1) / KX_PROD;
-      for (int j = 0; j <= rounds; ++j) {
-        if (!chainw) {
+      if (!chainw) {
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1, use = ground >> 1;
+          if (use > 0) mbar_wait(&S.empty[h], (use - 1) & 1);   // the chain warp has read this half's previous round
           const int tl = j * KX_PROD + warp;
-          if (j < rounds && tl < NTILE) {
+          if (tl < NTILE) {
             const int i = tl >> 3;
             const float4 GX = s_gx4[tl * 32 + lane], GY = s_gy4[tl * 32 + lane];
             float ab[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
-            float4* dst = s_ring + ((j & 1) * KX_PROD + warp) * KX_TILE_F4 + lane;
+            float4* dst = s_ring + (h * KX_PROD + warp) * KX_TILE_F4 + lane;
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             switch (pass) {
               case 0: kx_produce<0>(z4, GX, GY, ab, z4, true, dst); break;
@@ -299,15 +332,22 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
               default: kx_produce<3>(z4, GX, GY, ab, z4, true, dst); break;
             }
           }
-        } else if (j > 0) {
-          for (int w = 0; w < KX_PROD; ++w) {
-            const int tl = (j - 1) * KX_PROD + w;
-            if (tl < NTILE) kx_consume(s_ring + (((j - 1) & 1) * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
-          }
+          mbar_arrive(&S.full[h]);
+          ++ground;
         }
-        __syncthreads();
-      }
-      if (chainw) {
+      } else {
+        float sx = 0.0f, sy = 0.0f;
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1;
+          mbar_wait(&S.full[h], (ground >> 1) & 1);
+#pragma unroll
+          for (int w = 0; w < KX_PROD; ++w) {
+            const int tl = j * KX_PROD + w;
+            if (tl < NTILE) kx_consume(s_ring + (h * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
+          }
+          mbar_arrive(&S.empty[h]);
+          ++ground;
+        }
         const float rx = kx_finish(sx), ry = kx_finish(sy);
         if ((lane & 7) == 0) {
           const int q = 6 * pass + (lane >> 3);
@@ -339,53 +379,65 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     int it = 0;
     while (S.cont) {
       float sx = 0.0f, sy = 0.0f;
-      const int rounds = (NTILE + KX_PROD - 1) / KX_PROD;
-      // producer state: the new-frame rows of the tile of the coming round, fetched one round ahead so that the L2
-      // round trip is covered by the previous round's arithmetic and barrier
-      float la[5], lb[5];
-      float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool lvis = false;
+      if (!chainw) {
+        // producer state: the new-frame rows of the NEXT tile, fetched one tile ahead so that the L2 round trip is
+        // covered by the current tile's arithmetic
+        float la[5], lb[5];
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool lvis = false;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) la[r] = lb[r] = 0.0f;
-      auto fetch = [&](int tl) {
-        const int i = tl >> 3, rq = tl & 7;
-        const float4 pa = s_npl[2 * i];
-        lw = s_npl[2 * i + 1];
-        lvis = __float_as_int(pa.y) != 0;
-        if (lvis) {
-          const float* pI = Inew + (__float_as_int(pa.x) + (rq * 4 - 1) * width + lane);
+        for (int r = 0; r < 5; ++r) la[r] = lb[r] = 0.0f;
+        auto fetch = [&](int tl) {
+          const int i = tl >> 3, rq = tl & 7;
+          const float4 pa = s_npl[2 * i];
+          lw = s_npl[2 * i + 1];
+          lvis = __float_as_int(pa.y) != 0;
+          if (lvis) {
+            const float* pI = Inew + (__float_as_int(pa.x) + (rq * 4 - 1) * width + lane);
 #pragma unroll
-          for (int r = 0; r < 5; ++r) { la[r] = __ldg(pI + r * width); lb[r] = __ldg(pI + r * width - 1); }
-        }
-      };
-      if (!chainw && warp < NTILE) fetch(warp);
-      for (int j = 0; j <= rounds; ++j) {
-        if (!chainw) {
+            for (int r = 0; r < 5; ++r) { la[r] = __ldg(pI + r * width); lb[r] = __ldg(pI + r * width - 1); }
+          }
+        };
+        if (warp < NTILE) fetch(warp);
+        for (int j = 0; j < ROUNDS; ++j) {
           const int tl = j * KX_PROD + warp;
-          if (j < rounds && tl < NTILE) {
+          const int h = ground & 1, use = ground >> 1;
+          const bool have = tl < NTILE;
+          float4 pn4 = make_float4(0.f, 0.f, 0.f, 0.f), R = pn4, GX = pn4, GY = pn4;
+          float ab[12];
+          bool vis = false;
+          if (have) {
             const int i = tl >> 3;
-            float4 pn4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool vis = lvis;
+            vis = lvis;
             if (vis) {                   // util_getPatch (utilities.cpp:55-113), unfused, reference order
               pn4.x = ((lw.x * la[1] + lw.y * lb[1]) + lw.z * la[0]) + lw.w * lb[0];
               pn4.y = ((lw.x * la[2] + lw.y * lb[2]) + lw.z * la[1]) + lw.w * lb[1];
               pn4.z = ((lw.x * la[3] + lw.y * lb[3]) + lw.z * la[2]) + lw.w * lb[2];
               pn4.w = ((lw.x * la[4] + lw.y * lb[4]) + lw.z * la[3]) + lw.w * lb[3];
             }
-            if (j + 1 < rounds && tl + KX_PROD < NTILE) fetch(tl + KX_PROD);
-            const float4 R = s_ref4[tl * 32 + lane], GX = s_gx4[tl * 32 + lane], GY = s_gy4[tl * 32 + lane];
-            float ab[12];
+            if (tl + KX_PROD < NTILE) fetch(tl + KX_PROD);
+            R = s_ref4[tl * 32 + lane]; GX = s_gx4[tl * 32 + lane]; GY = s_gy4[tl * 32 + lane];
 #pragma unroll
             for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
-            kx_produce<4>(R, GX, GY, ab, pn4, vis, s_ring + ((j & 1) * KX_PROD + warp) * KX_TILE_F4 + lane);
           }
-        } else if (j > 0) {
-          for (int w = 0; w < KX_PROD; ++w) {
-            const int tl = (j - 1) * KX_PROD + w;
-            if (tl < NTILE) kx_consume(s_ring + (((j - 1) & 1) * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
-          }
+          // every producer keeps step with the ring, with or without a tile in this round (the arrival counts are per round)
+          if (use > 0) mbar_wait(&S.empty[h], (use - 1) & 1);
+          if (have) kx_produce<4>(R, GX, GY, ab, pn4, vis, s_ring + (h * KX_PROD + warp) * KX_TILE_F4 + lane);
+          mbar_arrive(&S.full[h]);
+          ++ground;
         }
-        __syncthreads();
+      } else {
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1;
+          mbar_wait(&S.full[h], (ground >> 1) & 1);
+#pragma unroll
+          for (int w = 0; w < KX_PROD; ++w) {
+            const int tl = j * KX_PROD + w;
+            if (tl < NTILE) kx_consume(s_ring + (h * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
+          }
+          mbar_arrive(&S.empty[h]);
+          ++ground;
+        }
       }
 
       if (chainw) {
