@@ -242,3 +242,52 @@ def test_pipelined_kernel_variant(ict, orc, monkeypatch):
     g0 = gpu_run(ict, case, trace_cap=48)
     assert np.array_equal(g["pt2d"], g0["pt2d"])
     assert np.array_equal(g["trace"][:, 0, 15], g0["trace"][:, 0, 15])
+
+
+# psz 32 has its own kernels (K2v2 for the default order, K2x for the reference order): their edge cases
+CASES32 = [
+    dict(seed=61, npts=1),                                   # one point: rank(H) <= 2, Eigen's truncated solve
+    dict(seed=62, npts=3, ntracks=5),                        # 24 tiles: the last round of K2x is partial
+    dict(seed=63, npts=7, ntracks=3),                        # 56 tiles = 8 full rounds; two groups per warp in K2v2
+    dict(seed=64, npts=9, maxpttrack=6, ntracks=2),          # more points than maxpttrack
+    dict(seed=65, npts=4, scale=3.0, ntracks=16),            # large motion: points leave the new frame
+    dict(seed=66, npts=5, donorm=1, ntracks=4),
+    dict(seed=67, npts=4, lv_f=2, lv_l=1, maxiter=3, ratio=0.1, ntracks=4),
+    dict(seed=68, npts=4, maxiter=1, ntracks=3),             # a single iteration per level
+]
+
+
+@pytest.mark.parametrize("kw", CASES32, ids=[str(i) for i in range(len(CASES32))])
+def test_psz32_kernels_edge_cases(ict, orc, kw):
+    case = make_case(psz=32, w=1280, h=704, **kw)
+    o = oracle_run(orc, case, trace_cap=48)
+    gx = gpu_run(ict, case, trace_cap=48, sum_order=1)       # K2x: bit for bit
+    assert np.array_equal(gx["pt2d"], o["pt2d"])
+    assert_bit_identical(gx, o)
+    g = gpu_run(ict, case, trace_cap=48)                     # K2v2: identical inputs -> J^T r to fp32 summation noise
+    assert np.array_equal(g["pt2d"], o["pt2d"])
+    res = check_parity(g, o, case, gates=False)
+    assert res["jtr_first"] <= 1e-5, res
+    assert np.array_equal(g["trace"][:, 0, 15], o["trace"][:, 0, 15])          # visible points, first iteration
+    gn = gpu_run(ict, case, trace_cap=0)                     # the production instantiation (no trace records)
+    assert np.array_equal(gn["p_out"], g["p_out"]) and np.array_equal(gn["iters"], g["iters"])
+    assert np.array_equal(gn["npixres"], g["npixres"])
+
+
+def test_psz32_kernels_points_out_of_view(ict, orc):
+    """An initial pose that moves a part of the points out of the reference image (template rows stay zero, the
+    coefficients stale) and others out of the new frame only at some levels."""
+    case = make_case(psz=32, w=1280, h=704, seed=69, npts=6, ntracks=12)
+    T = case["T"]
+    p_in = np.zeros((T, 6))
+    p_in[:, 0] = np.linspace(0.6, 2.4, T)                    # 150 .. 600 px to the right at level 0
+    p_in[:, 4] = 0.02
+    o = oracle_run(orc, case, trace_cap=48, p_in=p_in)
+    assert (o["trace"][:, 0, 15] < 6).any() and (o["trace"][:, 0, 15] > 0).any()   # some, not all, points visible
+    gx = gpu_run(ict, case, trace_cap=48, sum_order=1, p_in=p_in)
+    assert np.array_equal(gx["pt2d"], o["pt2d"])
+    assert_bit_identical(gx, o)
+    g = gpu_run(ict, case, trace_cap=48, p_in=p_in)
+    res = check_parity(g, o, case, gates=False)
+    assert res["jtr_first"] <= 1e-5, res
+    assert np.array_equal(g["trace"][:, 0, 15], o["trace"][:, 0, 15])
