@@ -26,13 +26,28 @@ def _stale(target, deps):
 
 
 def build_library(force=False, verbose=False):
+    """One object per translation unit (compiled in parallel, only the stale ones), then one link.  There is no
+    relocatable device code: no kernel calls a device function of another unit."""
     deps = [os.path.join(CSRC, d) for d in LIB_DEPS]
     if not force and not _stale(LIB, deps):
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in LIB_SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    headers = [d for d in deps if not d.endswith(".cu")]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for src in LIB_SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
+            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            jobs.append(cmd)
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, capture_output=not verbose, text=True), jobs):
+                if r.returncode:
+                    raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(r.args), (r.stderr or "")[-4000:]))
+    objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in LIB_SOURCES]
+    subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs, check=True)
     return LIB
 
 
