@@ -161,6 +161,17 @@ __device__ __forceinline__ void kx_consume(const float4* tile, int lane, bool fi
   sx = sx + x0.w; sy = sy + y0.w; sx = sx + x1.w; sy = sy + y1.w; sx = sx + x2.w; sy = sy + y2.w; sx = sx + x3.w; sy = sy + y3.w;
 }
 
+// One round: the tiles 7j .. 7j+6 of a ring half, in order.  A full round is straight-line code (no per-tile test),
+// so the loads of the later tiles are issued while the additions of the earlier ones are still in flight.
+__device__ __forceinline__ void kx_consume_round(const float4* half, int lane, int j, int ntile, float& sx, float& sy) {
+  if ((j + 1) * KX_PROD <= ntile) {
+#pragma unroll
+    for (int w = 0; w < KX_PROD; ++w) kx_consume(half + w * KX_TILE_F4, lane, w == 0 && j == 0, sx, sy);
+  } else {
+    for (int w = 0; j * KX_PROD + w < ntile; ++w) kx_consume(half + w * KX_TILE_F4, lane, w == 0 && j == 0, sx, sy);
+  }
+}
+
 // Eigen's redux tail for chains held one per lane in groups of eight: (c0+c4 + c2+c6) + (c1+c5 + c3+c7).
 // Returns the sum in the lanes with (lane & 7) == 0.
 __device__ __forceinline__ float kx_finish(float s) {
@@ -360,11 +371,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
           mbar_wait(&S.full[h], (ground >> 1) & 1);
-#pragma unroll
-          for (int w = 0; w < KX_PROD; ++w) {
-            const int tl = j * KX_PROD + w;
-            if (tl < NTILE) kx_consume(s_ring + (h * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
-          }
+          kx_consume_round(s_ring + h * KX_PROD * KX_TILE_F4, lane, j, NTILE, sx, sy);
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
@@ -450,11 +457,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
           mbar_wait(&S.full[h], (ground >> 1) & 1);
-#pragma unroll
-          for (int w = 0; w < KX_PROD; ++w) {
-            const int tl = j * KX_PROD + w;
-            if (tl < NTILE) kx_consume(s_ring + (h * KX_PROD + w) * KX_TILE_F4, lane, tl == 0, sx, sy);
-          }
+          kx_consume_round(s_ring + h * KX_PROD * KX_TILE_F4, lane, j, NTILE, sx, sy);
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
