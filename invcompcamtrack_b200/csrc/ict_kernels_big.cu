@@ -11,6 +11,8 @@
 #include "ict_kernels.cuh"
 #include "ict_device.cuh"
 
+#include <cstdlib>
+
 namespace ict {
 
 int64_t launch_count(int reset);
@@ -22,6 +24,7 @@ struct BigState {
   Lu6 lu;
   float normdp, normdp_init;
   int cont, it, nvis, trace_n, level_it;
+  unsigned ticket;          // CTAs that have published their partial sums in the running fused-iteration launch
   long long npix;
 };
 
@@ -37,8 +40,10 @@ struct BigWork {
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int big_ncta(int64_t E) {
+  // at most four 256-thread CTAs per SM (the streaming kernels use up to 64 registers): one resident wave, no tail.
+  // The grid fixes the partition of the two-stage sums, so every kernel of this file uses the same one.
   int64_t c = (E + 1023) / 1024;
-  if (c > 148 * 8) c = 148 * 8;
+  if (c > 148 * 4) c = 148 * 4;
   if (c < 1) c = 1;
   return (int)c;
 }
@@ -141,6 +146,7 @@ __global__ void k_big_init(const BigArgs a) {
     S->trace_n = 0;
     S->cont = 0;
     S->it = 0;
+    S->ticket = 0;
   }
 }
 
@@ -455,6 +461,184 @@ __global__ void __launch_bounds__(64) k_big_iter_sums_exact(const BigArgs a) {
     a.w.part[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, tid, e) * a.w.pnew[e]; }, Nfull, E);
 }
 
+// ==================================================================================================
+// Fused dense path: psz = 1 (one pixel per point), tree sums, no patch normalisation — BASELINE config 4.
+// The general kernels above keep 19 words of per-point state alive between launches (gx, gy, ten coefficients, four
+// weights, base, visibility) and need three launches per iteration.  With one pixel per point the six
+// steepest-descent values ARE per-point state, so the template is (ref, sd1..sd6) = 28 B per point, an iteration
+// streams 40 B per point (X, Y, Z, ref, sd) plus the four gathered texels — the 44 B per pixel-residual of SURVEY.md
+// §8(d) — and everything an iteration does fits one launch: project, place, sample, residual, six partial sums per
+// CTA, and the CTA that publishes its partials LAST (ticket counter) adds them in the fixed order, solves, updates
+// the pose and evaluates the stop rule.  Same per-element arithmetic, same thread partition and same summation order
+// as k_big_iter_points/elems/finish: results are bit-identical to that path (tests/test_gpu_parity.py).
+// ==================================================================================================
+__global__ void __launch_bounds__(256) k_dense_level(const BigArgs a, int sl) {
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  const int rf = a.prm.fixed_ref;
+  const float* __restrict__ Iref = a.prm.frames[rf].I[sl];
+  const float* __restrict__ Dxr = a.prm.frames[rf].dx[sl];
+  const float* __restrict__ Dyr = a.prm.frames[rf].dy[sl];
+  const long long P = a.P;
+  float* sdp = a.w.coef;                   // sd_k of point i at sdp[k * P + i] (the coefficient region, 10 P floats)
+  float acc[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    const float xc = a.w.Xc[i], yc = a.w.Yc[i], zc = a.w.Zc[i];
+    const float mx = (xc / zc) * fx + cx;
+    const float my = (yc / zc) * fy + cy;
+    const bool out = !((mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho));   // odometer.cpp:273-275
+    float sd[6];
+    if (!out) {
+      const PatchPlace q = patch_place(mx, my, a.prm.op.pszd2, width);      // util_getPatch_grad, one pixel
+      a.w.ref[i] = bilin4(Iref, q.base, width, q.w0, q.w1, q.w2, q.w3);
+      const float gx = bilin4(Dxr, q.base, width, q.w0, q.w1, q.w2, q.w3);
+      const float gy = bilin4(Dyr, q.base, width, q.w0, q.w1, q.w2, q.w3);
+      float c[10];
+      sd_coefs(xc, yc, zc, fx, fy, c);
+      sd_values(gx, gy, c, sd);                                              // odometer.cpp:317-326
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sdp[k * P + i] = sd[k];
+    } else {                               // out of the reference image: the previous level's values stay
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sd[k] = sdp[k * P + i];
+    }
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = p; q < 6; ++q) { acc[k] = acc[k] + sd[p] * sd[q]; ++k; }
+  }
+  cta_partials<21>(acc, a.w.part);
+}
+
+__global__ void __launch_bounds__(256, 4) k_dense_iter(const BigArgs a, int sl) {
+  BigState* S = a.w.st;
+  if (!S->cont) return;
+  __shared__ float s_G[12];
+  __shared__ float s_sum[8];
+  __shared__ int s_cnt[8];
+  __shared__ bool s_last;
+  if (threadIdx.x < 12) s_G[threadIdx.x] = S->G[threadIdx.x];
+  __syncthreads();
+  float G[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) G[k] = s_G[k];
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  const int64_t off = a.prm.pt_off[a.t];
+  const float* __restrict__ q = a.prm.pt3d + 3 * off;
+  const long long P = a.P;
+  const float* __restrict__ sdp = a.w.coef;
+  float acc[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+  int cnt = 0;
+  // Two points per trip: both points' streams (X, Y, Z, ref, sd1..6) and then both gathers are in flight together;
+  // the additions stay in point order, so the sums are those of the one-point loop.
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto sample = [&](long long i, float X, float Y, float Z, bool& vis) -> float {
+    const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];                    // project_pt, pose.cpp:307-397
+    const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
+    const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
+    const float mx = (tx / tz) * fx + cx;
+    const float my = (ty / tz) * fy + cy;
+    vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);                   // odometer.cpp:369-371
+    if (!vis) return 0.0f;
+    const PatchPlace pp = patch_place(mx, my, a.prm.op.pszd2, width);
+    return bilin4(Inew, pp.base, width, pp.w0, pp.w1, pp.w2, pp.w3);
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool hj = j < P;
+    const float X0 = q[i], Y0 = q[a.n_in + i], Z0 = q[2 * (int64_t)a.n_in + i];
+    const float X1 = hj ? q[j] : 0.0f, Y1 = hj ? q[a.n_in + j] : 0.0f, Z1 = hj ? q[2 * (int64_t)a.n_in + j] : 1.0f;
+    const float r0 = a.w.ref[i], r1 = hj ? a.w.ref[j] : 0.0f;
+    float s0[6], s1[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { s0[k] = sdp[k * P + i]; s1[k] = hj ? sdp[k * P + j] : 0.0f; }
+    bool v0, v1 = false;
+    const float pn0 = sample(i, X0, Y0, Z0, v0);
+    const float pn1 = hj ? sample(j, X1, Y1, Z1, v1) : 0.0f;
+    if (v0) {
+      const float pd = r0 - pn0;                                               // pdiff, odometer.cpp:381
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = acc[k] + s0[k] * pd;                 // sd_k_proj and its sum, :386-404
+      ++cnt;
+    }
+    if (hj && v1) {
+      const float pd = r1 - pn1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = acc[k] + s1[k] * pd;
+      ++cnt;
+    }
+  }
+  cta_partials<6>(acc, a.w.part);
+  // visible points of this CTA (integers: order-independent)
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __threadfence();                         // this CTA's partial sums are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) c += s_cnt[wv];
+    if (c) atomicAdd(&S->nvis, c);
+    __threadfence();
+    s_last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the last CTA: 9a fixed-order sum of the CTA partials, 9b solve, 10 update, stop rule -----------------------
+  __threadfence();
+  {
+    __shared__ float s_p[8 * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ncta = gridDim.x;
+    for (int k = 0; k < 6; ++k) {         // same order as finish_partials<6>; partials read past L1
+      float sm = 0.0f;
+      for (int c = threadIdx.x; c < ncta; c += blockDim.x) sm = sm + __ldcg(a.w.part + c * 21 + k);
+      sm = warp_sum(sm);
+      if (lane == 0) s_p[warp * 8 + k] = sm;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float sm = s_p[threadIdx.x];
+      for (int wv = 1; wv < nw; ++wv) sm = sm + s_p[wv * 8 + threadIdx.x];
+      s_sum[threadIdx.x] = sm;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const ict_optparam& op = a.prm.op;
+    float sumsd[6], dp[6];
+    for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
+    lu6_solve(S->lu, sumsd, dp);
+    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
+    se3_exp<float>(S->G, S->p);
+    const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
+    if (S->it == 0) S->normdp_init = normdp;
+    S->normdp = normdp;
+    const int nvis = *(volatile int*)&S->nvis;
+    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
+      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
+      rec[0] = (float)sl;
+      rec[1] = (float)S->it;
+      for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+      rec[14] = normdp;
+      rec[15] = (float)nvis;
+      for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+    }
+    S->npix += (long long)nvis * op.novals;
+    S->nvis = 0;
+    S->it += 1;
+    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+    S->ticket = 0;
+  }
+}
+
 __global__ void k_big_level_end(const BigArgs a, int sl) {
   const ict_optparam& op = a.prm.op;
   if (a.prm.iters) a.prm.iters[(int64_t)a.t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = a.w.st->it;
@@ -487,10 +671,17 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const int pcta = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
   const bool pn = op.dopatchnorm != 0;
   const bool ex = prm.sum_mode != 0;   // reference-order sums (patch means stay warp trees here)
+  const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !getenv("ICT_DENSE_V1");
   int nl = 0;
   k_big_init<<<ncta, 256, 0, st>>>(a); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
-  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+  for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
+    k_dense_level<<<ncta, 256, 0, st>>>(a, sl); ++nl;
+    k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
+    for (int it = 0; it < op.maxiter; ++it) { k_dense_iter<<<ncta, 256, 0, st>>>(a, sl); ++nl; }
+    k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
+  }
+  for (int sl = op.lv_f; sl >= op.lv_l && !fused; --sl) {
     k_big_level_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
     k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1); ++nl; }

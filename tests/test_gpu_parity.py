@@ -196,6 +196,12 @@ def test_dense_alignment_multi_cta_path(ict, orc, kw):
     assert np.abs(g["p_out"][0] - o["p_out"][0]).max() < 1e-3, res
     if kw["psz"] == 1:   # psz = 1 samples both images one pixel up-left: biased but it follows the motion
         assert np.abs(g["p_out"][0] - case["p_gt"]).max() < 0.25 * np.abs(case["p_gt"]).max()
+        # the fused dense kernels (one launch per iteration) against the general multi-CTA kernels in the same tree
+        # order: same per-element arithmetic, same partition, same summation order -> equal bits
+        gg = gpu_run(ict, case, trace_cap=48, sum_order=2)
+        assert np.array_equal(g["p_out"], gg["p_out"]) and np.array_equal(g["iters"], gg["iters"])
+        assert np.array_equal(g["npixres"], gg["npixres"])
+        assert np.array_equal(g["trace"][..., :16], gg["trace"][..., :16])
     print(res, g["iters"], o["iters"])
 
 
