@@ -460,6 +460,47 @@ static __device__ __noinline__ void lu6_solve(const Lu6& f, const float* b, floa
 #undef LU
 }
 
+// FullPivLU::solve (odometer.cpp:514) as straight-line code for any rank: lu6_solve of ict_device.cuh (c = P b,
+// unit-lower forward substitution over all six rows, upper backward substitution on the leading rank x rank block
+// with true divisions, zeros beyond the rank, x = Q c) with the permutations folded into the index tables and the
+// rank test as predicates — the same operations in the same order, hence the same bits; about 100 instructions
+// instead of the loops over run-time bounds and the local-memory array of the generic routine (37 % of the 4-point
+// benchmark tracks' level Hessians are rank-deficient by Eigen's threshold, so that path is not rare).
+__device__ __forceinline__ void lu6_solve_exact(const Lu6& f, const float* b, float* x) {
+#define LU(i, j) f.lu[(i) + 6 * (j)]
+  const int rank = f.rank;
+  float c0 = b[f.pr[0]], c1 = b[f.pr[1]], c2 = b[f.pr[2]], c3 = b[f.pr[3]], c4 = b[f.pr[4]], c5 = b[f.pr[5]];
+  if (rank == 0) c0 = c1 = c2 = c3 = c4 = c5 = 0.0f;
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  if (rank > 5) {
+    c5 = c5 / LU(5, 5);
+    c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  } else c5 = 0.0f;
+  if (rank > 4) {
+    c4 = c4 / LU(4, 4);
+    c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  } else c4 = 0.0f;
+  if (rank > 3) {
+    c3 = c3 / LU(3, 3);
+    c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  } else c3 = 0.0f;
+  if (rank > 2) {
+    c2 = c2 / LU(2, 2);
+    c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  } else c2 = 0.0f;
+  if (rank > 1) {
+    c1 = c1 / LU(1, 1);
+    c0 = c0 - c1 * LU(0, 1);
+  } else c1 = 0.0f;
+  c0 = rank > 0 ? c0 / LU(0, 0) : 0.0f;
+  x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
+#undef LU
+}
+
 // Production-kernel variant of lu6_solve_full: the six divisions by the pivots become multiplications by their
 // (correctly rounded, once per level) reciprocals.  Differs from the reference's x / u by at most one ulp per
 // division — far below what the fp32 right-hand side carries — and removes six ~10-deep dependent chains from
@@ -736,5 +777,40 @@ __device__ __forceinline__ void warp_sum6_store(const float* acc, float* dst /* 
     for (int j = 0; j < 3; ++j) dst[base + j] = v[j];
   }
 }
+
+// ---- shared-memory barriers (mbarrier) and bulk asynchronous copies (sm_90+ PTX) ----------------------------------------
+__device__ __forceinline__ unsigned ict_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ict_saddr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {   // release at CTA scope
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ict_saddr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {   // acquire at CTA scope
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "KX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra KX_DONE;\n"
+      "bra KX_WAIT;\n"
+      "KX_DONE:\n"
+      "}\n" ::"r"(ict_saddr(b)), "r"(parity)
+      : "memory");
+}
+
+// producer side of a bulk copy: the barrier's phase completes when `bytes` have landed (and the one arrival is in)
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ict_saddr(b)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy through the copy engine of the SM (TMA, non-tensor form): 16-byte aligned addresses,
+// size a multiple of 16; completion is signalled on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ict_saddr(dst)),
+               "l"(src), "r"(bytes), "r"(ict_saddr(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 }  // namespace ict

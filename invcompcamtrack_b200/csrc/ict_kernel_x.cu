@@ -37,27 +37,6 @@ void count_launch_external();
 #define KX_PROD 7                       /* producer warps; warp KX_PROD is the chain warp */
 #define KX_TILE_F4 (6 * 32)             /* float4 per staged tile: six quantities x 32 columns (x 4 rows) */
 
-// ---- shared-memory barriers (mbarrier) for the producer -> chain hand-off of ring slots ---------------------------------
-__device__ __forceinline__ unsigned kx_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kx_saddr(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {   // release at CTA scope
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kx_saddr(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {   // acquire at CTA scope
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "KX_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra KX_DONE;\n"
-      "bra KX_WAIT;\n"
-      "KX_DONE:\n"
-      "}\n" ::"r"(kx_saddr(b)), "r"(parity)
-      : "memory");
-}
-
 // Producer-side wait: poll with a back-off.  A producer is a round ahead of the chain warp most of the time; a tight
 // try_wait loop (SYNCS + YIELD + BRA) was 29 % of all issued instructions (ncu).  Backing off costs nothing (the
 // chain warp is the critical resource) and leaves the issue slots to it.
@@ -71,7 +50,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* b, unsigne
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n"
         : "=r"(done)
-        : "r"(kx_saddr(b)), "r"(parity)
+        : "r"(ict_saddr(b)), "r"(parity)
         : "memory");
     if (done) break;
     __nanosleep(128);
@@ -179,47 +158,6 @@ __device__ __forceinline__ float kx_finish(float s) {
   const float p0 = s + __shfl_down_sync(FULL, s, 4);        // lanes c < 4: ch[c] + ch[c+4]
   const float t = p0 + __shfl_down_sync(FULL, p0, 2);       // lane c = 0: p0[0] + p0[2]; c = 1: p0[1] + p0[3]
   return t + __shfl_down_sync(FULL, t, 1);
-}
-
-// FullPivLU::solve (odometer.cpp:514) as straight-line code for any rank: lu6_solve of ict_device.cuh (c = P b,
-// unit-lower forward substitution over all six rows, upper backward substitution on the leading rank x rank block
-// with true divisions, zeros beyond the rank, x = Q c) with the permutations folded into the index tables and the
-// rank test as predicates — the same operations in the same order, hence the same bits; about 100 instructions
-// instead of the loops over run-time bounds and the local-memory array of the generic routine (37 % of the 4-point
-// benchmark tracks' level Hessians are rank-deficient by Eigen's threshold, so that path is not rare).
-__device__ __forceinline__ void lu6_solve_exact(const Lu6& f, const float* b, float* x) {
-#define LU(i, j) f.lu[(i) + 6 * (j)]
-  const int rank = f.rank;
-  float c0 = b[f.pr[0]], c1 = b[f.pr[1]], c2 = b[f.pr[2]], c3 = b[f.pr[3]], c4 = b[f.pr[4]], c5 = b[f.pr[5]];
-  if (rank == 0) c0 = c1 = c2 = c3 = c4 = c5 = 0.0f;
-  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
-  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
-  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
-  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
-  c5 = c5 - c4 * LU(5, 4);
-  if (rank > 5) {
-    c5 = c5 / LU(5, 5);
-    c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
-  } else c5 = 0.0f;
-  if (rank > 4) {
-    c4 = c4 / LU(4, 4);
-    c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
-  } else c4 = 0.0f;
-  if (rank > 3) {
-    c3 = c3 / LU(3, 3);
-    c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
-  } else c3 = 0.0f;
-  if (rank > 2) {
-    c2 = c2 / LU(2, 2);
-    c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
-  } else c2 = 0.0f;
-  if (rank > 1) {
-    c1 = c1 / LU(1, 1);
-    c0 = c0 - c1 * LU(0, 1);
-  } else c1 = 0.0f;
-  c0 = rank > 0 ? c0 / LU(0, 0) : 0.0f;
-  x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
-#undef LU
 }
 
 __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {

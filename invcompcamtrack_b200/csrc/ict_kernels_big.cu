@@ -514,13 +514,92 @@ __global__ void __launch_bounds__(256) k_dense_level(const BigArgs a, int sl) {
   cta_partials<21>(acc, a.w.part);
 }
 
+// Shared tail of the dense iteration kernels: CTA partial sums, visible-point count, ticket; the CTA that arrives last
+// adds the partials in the fixed order, solves, updates the pose and evaluates the stop rule.
+__device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, float* acc, int cnt) {
+  BigState* S = a.w.st;
+  __shared__ float s_sum[8];
+  __shared__ int s_cnt[8];
+  __shared__ bool s_last;
+  cta_partials<6>(acc, a.w.part);
+  // visible points of this CTA (integers: order-independent)
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __threadfence();                         // this CTA's partial sums are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) c += s_cnt[wv];
+    if (c) atomicAdd(&S->nvis, c);
+    __threadfence();
+    s_last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the last CTA: 9a fixed-order sum of the CTA partials, 9b solve, 10 update, stop rule -----------------------
+  __threadfence();
+  {
+    __shared__ float s_p[8 * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ncta = gridDim.x;
+    // same order as finish_partials<6> (per thread: CTAs tid, tid + 256, ... ascending; warp tree; warps ascending);
+    // all of a thread's partials are loaded (past L1) before the first addition: one L2 round trip, not eighteen
+    float v[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = threadIdx.x + j * 256;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[j][k] = c < ncta ? __ldcg(a.w.part + c * 21 + k) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float sm = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (threadIdx.x + j * 256 < ncta) sm = sm + v[j][k];
+      for (int c = threadIdx.x + 768; c < ncta; c += blockDim.x) sm = sm + __ldcg(a.w.part + c * 21 + k);
+      sm = warp_sum(sm);
+      if (lane == 0) s_p[warp * 8 + k] = sm;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float sm = s_p[threadIdx.x];
+      for (int wv = 1; wv < nw; ++wv) sm = sm + s_p[wv * 8 + threadIdx.x];
+      s_sum[threadIdx.x] = sm;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const ict_optparam& op = a.prm.op;
+    float sumsd[6], dp[6];
+    for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
+    lu6_solve_exact(S->lu, sumsd, dp);   // == lu6_solve, straight-line
+    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
+    se3_exp<float>(S->G, S->p);
+    const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
+    if (S->it == 0) S->normdp_init = normdp;
+    S->normdp = normdp;
+    const int nvis = *(volatile int*)&S->nvis;
+    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
+      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
+      rec[0] = (float)sl;
+      rec[1] = (float)S->it;
+      for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+      rec[14] = normdp;
+      rec[15] = (float)nvis;
+      for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+    }
+    S->npix += (long long)nvis * op.novals;
+    S->nvis = 0;
+    S->it += 1;
+    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+    S->ticket = 0;
+  }
+}
+
 __global__ void __launch_bounds__(256, 4) k_dense_iter(const BigArgs a, int sl) {
   BigState* S = a.w.st;
   if (!S->cont) return;
   __shared__ float s_G[12];
-  __shared__ float s_sum[8];
-  __shared__ int s_cnt[8];
-  __shared__ bool s_last;
   if (threadIdx.x < 12) s_G[threadIdx.x] = S->G[threadIdx.x];
   __syncthreads();
   float G[12];
@@ -577,66 +656,90 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter(const BigArgs a, int sl) 
       ++cnt;
     }
   }
-  cta_partials<6>(acc, a.w.part);
-  // visible points of this CTA (integers: order-independent)
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __threadfence();                         // this CTA's partial sums are visible before its ticket is
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int c = 0;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) c += s_cnt[wv];
-    if (c) atomicAdd(&S->nvis, c);
-    __threadfence();
-    s_last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
+  dense_iter_finish(a, sl, acc, cnt);
+}
+
+// The same iteration with the five streams of a point (X, Y, Z, ref, sd1..6: 40 B) staged through shared memory by
+// bulk asynchronous copies (cp.async.bulk, the copy engine behind TMA) three tiles of 256 points ahead: the DRAM round
+// trip of the streams is off the threads' critical path, which keeps only the projection, the placement and the
+// four-texel gather (two tiles per trip, for more gathers in flight, was not faster: 35 vs 33 us).  CTA b takes the tiles b, b + G, b + 2G, ... and thread t the point t of each — the partition
+// and order of the grid-stride loop above, hence the same sums bit for bit.  Needs 16-byte aligned streams
+// (point count a multiple of 4); the launcher falls back to k_dense_iter otherwise.
+#define DENSE_NST 3
+__global__ void __launch_bounds__(256, 4) k_dense_iter_tma(const BigArgs a, int sl) {
+  BigState* S = a.w.st;
+  if (!S->cont) return;
+  __shared__ __align__(128) float s_buf[DENSE_NST][10][256];
+  __shared__ unsigned long long s_full[DENSE_NST];
+  __shared__ float s_G[12];
+  const int tid = threadIdx.x;
+  if (tid < 12) s_G[tid] = S->G[tid];
+  if (tid == 0) {
+    for (int k = 0; k < DENSE_NST; ++k) mbar_init(&s_full[k], 1);
+    mbar_fence_init();
   }
   __syncthreads();
-  if (!s_last) return;
-  // ---- the last CTA: 9a fixed-order sum of the CTA partials, 9b solve, 10 update, stop rule -----------------------
-  __threadfence();
-  {
-    __shared__ float s_p[8 * 8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ncta = gridDim.x;
-    for (int k = 0; k < 6; ++k) {         // same order as finish_partials<6>; partials read past L1
-      float sm = 0.0f;
-      for (int c = threadIdx.x; c < ncta; c += blockDim.x) sm = sm + __ldcg(a.w.part + c * 21 + k);
-      sm = warp_sum(sm);
-      if (lane == 0) s_p[warp * 8 + k] = sm;
+  float G[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) G[k] = s_G[k];
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  const int64_t off = a.prm.pt_off[a.t];
+  const float* q = a.prm.pt3d + 3 * off;
+  const long long P = a.P;
+  const float* sdp = a.w.coef;
+  const int ntile = (int)((P + 255) / 256);
+  const int nmine = ntile > (int)blockIdx.x ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto issue = [&](int n) {               // thread 0: the n-th tile of this CTA into stage n % NST
+    const long long i0 = ((long long)blockIdx.x + (long long)n * gridDim.x) * 256;
+    const unsigned bytes = (unsigned)((P - i0 < 256 ? P - i0 : 256) * 4);
+    const int st = n % DENSE_NST;
+    mbar_expect_tx(&s_full[st], 10 * bytes);
+    bulk_g2s(s_buf[st][0], q + i0, bytes, &s_full[st]);
+    bulk_g2s(s_buf[st][1], q + a.n_in + i0, bytes, &s_full[st]);
+    bulk_g2s(s_buf[st][2], q + 2 * (int64_t)a.n_in + i0, bytes, &s_full[st]);
+    bulk_g2s(s_buf[st][3], a.w.ref + i0, bytes, &s_full[st]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bulk_g2s(s_buf[st][4 + k], sdp + k * P + i0, bytes, &s_full[st]);
+  };
+  if (tid == 0)
+    for (int n = 0; n < DENSE_NST && n < nmine; ++n) issue(n);
+  float acc[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
+  int cnt = 0;
+  // one point of a staged tile: projection, placement, the four-texel gather (returns the sample, sets vis)
+  auto sample = [&](int st, bool& vis) -> float {
+    const float X = s_buf[st][0][tid], Y = s_buf[st][1][tid], Z = s_buf[st][2][tid];
+    const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];                    // project_pt, pose.cpp:307-397
+    const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
+    const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
+    const float mx = (tx / tz) * fx + cx;
+    const float my = (ty / tz) * fy + cy;
+    vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);                   // odometer.cpp:369-371
+    if (!vis) return 0.0f;
+    const PatchPlace pp = patch_place(mx, my, a.prm.op.pszd2, width);
+    return bilin4(Inew, pp.base, width, pp.w0, pp.w1, pp.w2, pp.w3);
+  };
+  for (int n = 0; n < nmine; ++n) {
+    const int st = n % DENSE_NST;
+    const long long i = ((long long)blockIdx.x + (long long)n * gridDim.x) * 256 + tid;
+    mbar_wait(&s_full[st], (n / DENSE_NST) & 1);
+    bool vis = false;
+    float pn = 0.0f;
+    if (i < P) pn = sample(st, vis);
+    if (vis) {
+      const float pd = s_buf[st][3][tid] - pn;                                 // pdiff, odometer.cpp:381
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[k] = acc[k] + s_buf[st][4 + k][tid] * pd;   // sd_k_proj and its sum, :386-404
+      ++cnt;
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      float sm = s_p[threadIdx.x];
-      for (int wv = 1; wv < nw; ++wv) sm = sm + s_p[wv * 8 + threadIdx.x];
-      s_sum[threadIdx.x] = sm;
-    }
-    __syncthreads();
+    __syncthreads();                       // every thread has read the stage
+    if (tid == 0 && n + DENSE_NST < nmine) issue(n + DENSE_NST);
   }
-  if (threadIdx.x == 0) {
-    const ict_optparam& op = a.prm.op;
-    float sumsd[6], dp[6];
-    for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
-    lu6_solve(S->lu, sumsd, dp);
-    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
-    se3_exp<float>(S->G, S->p);
-    const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
-    if (S->it == 0) S->normdp_init = normdp;
-    S->normdp = normdp;
-    const int nvis = *(volatile int*)&S->nvis;
-    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
-      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
-      rec[0] = (float)sl;
-      rec[1] = (float)S->it;
-      for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
-      rec[14] = normdp;
-      rec[15] = (float)nvis;
-      for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
-    }
-    S->npix += (long long)nvis * op.novals;
-    S->nvis = 0;
-    S->it += 1;
-    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
-    S->ticket = 0;
-  }
+  dense_iter_finish(a, sl, acc, cnt);
 }
 
 __global__ void k_big_level_end(const BigArgs a, int sl) {
@@ -678,7 +781,12 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
     k_dense_level<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
-    for (int it = 0; it < op.maxiter; ++it) { k_dense_iter<<<ncta, 256, 0, st>>>(a, sl); ++nl; }
+    // bulk-copy staging needs 16-byte aligned streams: point counts and the track's offset multiples of four
+    const bool tma = t == 0 && (a.P % 4 == 0) && (a.n_in % 4 == 0) && !getenv("ICT_DENSE_LDG");   // t == 0: offset 0
+    for (int it = 0; it < op.maxiter; ++it) {
+      if (tma) k_dense_iter_tma<<<ncta, 256, 0, st>>>(a, sl); else k_dense_iter<<<ncta, 256, 0, st>>>(a, sl);
+      ++nl;
+    }
     k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
   }
   for (int sl = op.lv_f; sl >= op.lv_l && !fused; --sl) {
