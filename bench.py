@@ -138,6 +138,61 @@ def cpu_sample(wl, op_kw, S, T, P, psz, w, h, lv_f, seqs, threads, use_ref, spre
                 alt=alt)
 
 
+def other_configs(ict, dev):
+    """The other BASELINE configs, timed once each through the same library (secondary numbers, not the headline):
+    configs[3] dense full-frame alignment at 1080p, configs[1] one 100-point template chain over 100 frames."""
+    import torch
+    from invcompcamtrack_b200 import synth
+    out = {}
+    # ---- configs[3]: dense, one point per pixel, psz 1, tilted plane (per-pixel depth) ----------------------------
+    w, h = 1920, 1080
+    sc, A, B, p_gt = synth.make_pair(41, w, h, tilt=(0.05, -0.03))
+    pts = sc.dense_points(16)
+    n = pts.size // 3
+    op = ict.make_optparam(lv_f=3, lv_l=0, psz=1, maxiter=10, normdp_ratio=0.01, donorm=0, dopatchnorm=0, maxpttrack=n)
+    fr = ict.Frames(2, w, h, 3, 1)
+    fr.upload(0, np.stack([A, B]))
+    tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_points(np.array([0, n], np.int64), pts.copy())
+    best = None
+    for rep in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = tr.track_batch(fr, 0, 1, np.zeros((1, 6)))
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    npix = int(r["npixres"].sum())
+    iters = int(r["iters"].sum())
+    out["dense_1080p"] = {"workload": "BASELINE configs[3]: %d points (one per pixel), psz 1, 4 levels, %d GN iterations"
+                          % (n, iters), "ms_per_trackpose": 1e3 * best, "value": npix / best,
+                          "unit": "pixel-residuals/s", "algorithmic_GBps": 44.0 * npix / best / 1e9,
+                          "note": "host call incl. launches and result copy; 44 B per pixel-residual (SURVEY.md 8d); "
+                                  "per-iteration kernel: profiles/r01_dense_launches.csv"}
+    tr.close(); fr.close()
+    # ---- configs[1]: run_track_nposes-style chain, 100 frames, 640x480, psz 8, 100 points; 256 pose samples ----
+    NF, S = 100, 256
+    sc, frames, poses = synth.make_sequence(5, NF, 640, 480)
+    op = ict.make_optparam(lv_f=3, lv_l=0, psz=8, maxiter=10, normdp_ratio=0.01, donorm=0, dopatchnorm=0, maxpttrack=100)
+    fr = ict.Frames(NF, 640, 480, 3, 8)
+    fr.upload(0, np.stack(frames))
+    tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_points(np.arange(S + 1, dtype=np.int64) * 100, np.concatenate([sc.points(100 + s_, 100, 8, 3) for s_ in range(S)]))
+    best = None
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = tr.track_sequence(fr, 0, NF - 1, 1, np.zeros((S, 6)))
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    out["chain_100_frames"] = {"workload": "BASELINE configs[1]: %d pose samples x one 100-point template chained over %d "
+                               "frames of 640x480, psz 8, 4 levels" % (S, NF), "ms_per_chain_batch": 1e3 * best,
+                               "tracks_per_s": S * (NF - 1) / best, "value": int(r["npixres"].sum()) / best,
+                               "unit": "pixel-residuals/s",
+                               "drift_vs_ground_truth": float(np.abs(r["poses"][-1, 0] - poses[-1]).max())}
+    tr.close(); fr.close()
+    return out
+
+
 KERNEL_NAME = "k_track_v2<16,4,false>"   # the production kernel for psz 32 (ict_kernel_v2.cu)
 
 
@@ -454,6 +509,10 @@ def main():
                                                "tracks": int(n), "ms": x_ms,
                                                "value": float(x_npix.sum().item()) / (x_ms * 1e-3),
                                                "unit": "pixel-residuals/s"}}}
+            try:
+                line["other_configs"] = other_configs(ict, dev)
+            except Exception as e:          # secondary numbers must never cost the headline line
+                line["other_configs"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
