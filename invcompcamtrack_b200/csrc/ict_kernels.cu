@@ -1236,6 +1236,8 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
   int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
   const int mode = (prm.op.dopatchnorm ? 1 : 0) | (prm.sum_mode ? 2 : 0);
   if (const char* e = getenv("ICT_NT")) nt = atoi(e);   // profiling knob
+  if ((mode & 2) == 0 && !prm.force_general && !getenv("ICT_FAST_V1") && v8_supported(prm.op, max_pts))
+    return launch_track_v8(prm, max_pts, stream);      // K2v8: 8x8 patches, with or without dopatchnorm
   if (mode == 0 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_FAST_V1") &&
       v2_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
     return launch_track_v2(prm, max_pts, stream);
