@@ -417,7 +417,10 @@ bool v8_supported(const ict_optparam& op, int max_pts) {
 
 template <bool PN, bool TRACE>
 static cudaError_t launch_v8_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};            // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track_v8<PN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);

@@ -482,7 +482,10 @@ cudaError_t launch_track_x(const TrackParams& prm, int max_pts, cudaStream_t str
   if (prm.T <= 0) return cudaSuccess;
   const size_t smem = kx_smem_bytes(prm.op, max_pts);
   if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};            // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track_x, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

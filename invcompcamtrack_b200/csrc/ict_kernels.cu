@@ -1157,7 +1157,10 @@ static size_t fast_smem_bytes(const ict_optparam& op, int max_pts) {
 
 template <int PSZ, int KTMAX, int MINB>
 static cudaError_t launch_track_fast_v(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};            // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track_fast<PSZ, KTMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
@@ -1205,7 +1208,10 @@ size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode) {
 
 template <int PSZ, int MODE>
 static cudaError_t launch_track_t(const TrackParams& prm, size_t smem, int nt, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};            // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track<PSZ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
