@@ -452,7 +452,12 @@ def main():
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_pixel_residual": BYTES_PER_PIXRES,
                              "kernel_ms_per_launch": ms_kernel,
-                             "kernel_share_of_step": ms_kernel / (ms_total / a.steps)},
+                             "kernel_share_of_step": ms_kernel / (ms_total / a.steps),
+                             "note": "achieved = algorithmic bytes (32 B per pixel-residual) / kernel time: the template "
+                                     "is resident in shared memory, so measured DRAM traffic (`traffic`, ncu) is ~0.1 % "
+                                     "of it and frac > 1; the kernel is issue/latency-bound (issue slots 58 % busy, "
+                                     "profiles/r01_k_track_v2_ncu_summary.txt). The HBM-streaming kernel of the path is "
+                                     "the dense iteration (other_configs.dense_1080p: 49 % of the measured bandwidth)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if e2e:
             line["e2e"] = {"value": npix_job * a.steps / (ms_e2e_all * 1e-3), "unit": "pixel-residuals/s",
