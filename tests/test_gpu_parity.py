@@ -348,3 +348,49 @@ def test_psz8_kernel_points_out_of_view(ict, orc):
     res = check_parity(g, o, case, gates=False)
     assert res["jtr_first"] <= 1e-5, res
     assert np.array_equal(g["trace"][:, 0, 15], o["trace"][:, 0, 15])
+
+
+def test_full_size_batch_properties(ict, orc):
+    """BASELINE config 3 at full size (4096 four-point 32x32 tracks on one 1080p pair): size-independent properties of
+    the production path — a track's result does not depend on its position in the batch, on the batch it is in, or on
+    the run (bit for bit), and a sample agrees with the oracle like the small
+    batches do (bit-identical in reference order)."""
+    case = make_case(seed=91, w=1920, h=1080, psz=32, npts=4, ntracks=4096)
+    T, P = case["T"], case["npts"]
+    op = ict.OptParam.from_buffer_copy(bytes(case["op"]))
+    fr = ict.Frames(2, case["w"], case["h"], case["lv_f"], case["psz"])
+    fr.upload(0, np.stack([case["A"], case["B"]]))
+
+    def run(order, sum_order=0):
+        tr = ict.Tracker(op, case["sc"].fc, case["sc"].cc, case["sc"].wh)
+        tr.set_sum_order(sum_order)
+        pts = case["pts"].reshape(T, 3 * P)[order].reshape(-1).copy()
+        tr.set_points(np.arange(len(order) + 1, dtype=np.int64) * P, pts)
+        out = tr.track_batch(fr, 0, 1, np.zeros((len(order), 6)))
+        tr.close()
+        return out
+
+    ident = np.arange(T)
+    a = run(ident)
+    b = run(ident)                                           # determinism
+    assert np.array_equal(a["p_out"], b["p_out"]) and np.array_equal(a["iters"], b["iters"])
+    perm = np.random.default_rng(5).permutation(T)           # position in the batch
+    c = run(perm)
+    assert np.array_equal(c["p_out"], a["p_out"][perm]) and np.array_equal(c["iters"], a["iters"][perm])
+    assert np.array_equal(c["npixres"], a["npixres"][perm])
+    h1, h2 = run(ident[:1500]), run(ident[1500:])            # the batch a track is in
+    assert np.array_equal(np.concatenate([h1["p_out"], h2["p_out"]]), a["p_out"])
+    # (recovering the ground-truth motion is not a property of this workload: a third of the 4-point Hessians are
+    # rank-deficient by Eigen's threshold and the reference's truncated solve then leaves pose components untouched)
+    # a sample of 64 tracks against the oracle: reference order bit for bit, default order on identical inputs
+    sub = ident[::64]
+    sc = dict(case, pts=case["pts"].reshape(T, 3 * P)[sub].reshape(-1).copy(),
+              pt_off=np.arange(len(sub) + 1, dtype=np.int64) * P, T=len(sub))
+    o = oracle_run(orc, sc, trace_cap=0)
+    x = run(sub, sum_order=1)
+    assert np.array_equal(x["p_out"], o["p_out"]) and np.array_equal(x["iters"], o["iters"])
+    assert np.array_equal(x["npixres"], o["npixres"])
+    xs = run(ident, sum_order=1)                             # ... and the sample is the same inside the full batch
+    assert np.array_equal(xs["p_out"][sub], x["p_out"])
+    assert np.median(np.abs(a["p_out"][sub] - o["p_out"]).max(axis=1)) < 1e-4   # default order: same poses in the median
+    fr.close()
