@@ -23,6 +23,7 @@
 #include "ict_kernels.cuh"
 #include "ict_device.cuh"
 #include "ict_kernel_v2.cuh"
+#include "ict_kernel_v8.cuh"
 
 #include <cstdlib>
 
@@ -31,35 +32,6 @@ namespace ict {
 void count_launch_external();
 
 #define V8_MP 16                        /* point slots per warp: up to 8 * 16 = 128 points per track */
-
-// the three rows a lane needs of one plane: rows 2j-1, 2j, 2j+1 at columns c and c-1 (o = offset of row 2j-1, col c)
-struct V8Rows { float a0, b0, a1, b1, a2, b2; };
-__device__ __forceinline__ V8Rows v8_load(const float* __restrict__ pl, int o, int width) {
-  V8Rows r;
-  r.a0 = __ldg(pl + o);             r.b0 = __ldg(pl + o - 1);
-  r.a1 = __ldg(pl + o + width);     r.b1 = __ldg(pl + o + width - 1);
-  r.a2 = __ldg(pl + o + 2 * width); r.b2 = __ldg(pl + o + 2 * width - 1);
-  return r;
-}
-// util_getPatch_grad (utilities.cpp:160-185), unfused, reference order: the lane's two pixels
-__device__ __forceinline__ float2 v8_bilin_exact(const V8Rows& r, const float4 w) {
-  float2 v;
-  v.x = ((w.x * r.a1 + w.y * r.b1) + w.z * r.a0) + w.w * r.b0;
-  v.y = ((w.x * r.a2 + w.y * r.b2) + w.z * r.a1) + w.w * r.b1;
-  return v;
-}
-// util_getPatch (utilities.cpp:107) with fused multiply-adds in the same association order
-__device__ __forceinline__ float2 v8_bilin_fma(const V8Rows& r, const float4 w) {
-  float2 v;
-  v.x = fmaf(w.w, r.b0, fmaf(w.z, r.a0, fmaf(w.y, r.b1, w.x * r.a1)));
-  v.y = fmaf(w.w, r.b1, fmaf(w.z, r.a1, fmaf(w.y, r.b2, w.x * r.a2)));
-  return v;
-}
-__device__ __forceinline__ float v8_warp_total(float v) {   // butterfly: every lane gets the total, fixed order
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // 16 per-lane values -> their 16 warp totals, total q in lanes 2q and 2q+1 (halving butterfly: 15 + 1 shuffles)
 __device__ __forceinline__ float v8_reduce16(const float* v) {

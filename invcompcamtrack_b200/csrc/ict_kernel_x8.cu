@@ -1,0 +1,424 @@
+// ict_kernel_x8.cu — K2x8: SetPose + TrackPose for 8x8 patches with the REFERENCE'S ORDER OF SUMMATION
+// (ict_tracker_set_sum_order(tr, 1)), with or without dopatchnorm: bit-identical to the oracle's default model of
+// the reference like k_track<8, 2|3> (ict_kernels.cu), organised like K2x (ict_kernel_x.cu) so that the sequential
+// chains do not leave the CTA idle — the reference's own configuration (psz 8, ~100 points per track) ran at 14 ms
+// per TrackPose in that mode with one thread per chain.
+//
+// With e = point*64 + row*8 + col, chain c of Eigen's packet sum IS column c: it adds rows 0..7 of point 0, then of
+// point 1, ...  A tile is one patch.  Producer warp w makes the patches 7j + w (round j): lane l takes the pixels
+// (2q, c) and (2q+1, c), q = l/8, c = l%8 (the K2v8 lane layout), computes the six values to be summed of both
+// pixels with the reference's roundings and stores them as stage[k][c][row]; the chain warp's lane (k, c) reads its
+// column with two LDS.128 and performs the eight additions of the patch in row order.  Ring halves of seven
+// patches are handed over with mbarriers as in K2x.  Every producer computes the placement of ITS patches with
+// lanes = patches after the iteration barrier, so the chain warp — the critical resource — only combines the chains,
+// solves (Eigen's elimination, straight-line, true divisions) and evaluates the reference's exp.
+//
+// dopatchnorm in the reference order: the mean of a patch is Eigen's sum of its 64 values, i.e. the same eight
+// column chains followed by the redux tail; a patch lives in one warp, so the chain of column c runs through the four
+// lanes that hold its rows (three shuffles) and the tail through the last row group's lanes.
+#include "ict_kernels.cuh"
+#include "ict_device.cuh"
+#include "ict_kernel_v2.cuh"
+#include "ict_kernel_v8.cuh"
+#include "ict_kernel_x.cuh"
+
+namespace ict {
+
+void count_launch_external();
+
+#define X8_TILE 384                     /* floats per staged patch: six quantities x 8 columns x 8 rows */
+#define X8_MAXR 32                      /* rounds per sum at most: 7 * 32 = 224 points per track */
+
+// Eigen's vectorised sum of the 64 values of a patch held two per lane (rows 2q, 2q+1 of column c; lane = 8q + c):
+// chain c = ((((v[0][c] + v[1][c]) + v[2][c]) + ...) + v[7][c]), then (c0+c4 + c2+c6) + (c1+c5 + c3+c7).
+// Returns the sum in every lane.
+__device__ __forceinline__ float x8_patch_sum(float a, float b) {
+  const unsigned FULL = 0xffffffffu;
+  const int q = (threadIdx.x & 31) >> 3;
+  float s = a + b;                                        // rows 0, 1 (valid in row group 0)
+#pragma unroll
+  for (int step = 1; step < 4; ++step) {
+    const float t = __shfl_up_sync(FULL, s, 8);
+    if (q == step) s = (t + a) + b;
+  }
+  // lanes 24..31 hold the chains of columns 0..7
+  const float p0 = s + __shfl_down_sync(FULL, s, 4);      // lanes 24..27: ch[c] + ch[c+4]
+  const float t2 = p0 + __shfl_down_sync(FULL, p0, 2);    // lane 24: p0[0] + p0[2]; lane 25: p0[1] + p0[3]
+  const float r = t2 + __shfl_down_sync(FULL, t2, 1);     // lane 24
+  return __shfl_sync(FULL, r, 24);
+}
+
+// chain warp, one staged patch: chain (k, c) adds rows 0..7 of column c
+__device__ __forceinline__ void x8_consume(const float* tile, int lane, bool first, float& sx, float& sy) {
+  const int c = lane & 7, kx = lane >> 3;
+  const float4* px = reinterpret_cast<const float4*>(tile + (kx * 8 + c) * 8);
+  const float4* py = reinterpret_cast<const float4*>(tile + ((4 + kx) * 8 + c) * 8);
+  const float4 x0 = px[0], x1 = px[1];
+  float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+  if (lane < 16) { y0 = py[0]; y1 = py[1]; }
+  sx = first ? x0.x : sx + x0.x;  sy = first ? y0.x : sy + y0.x;
+  sx = sx + x0.y; sy = sy + y0.y; sx = sx + x0.z; sy = sy + y0.z; sx = sx + x0.w; sy = sy + y0.w;
+  sx = sx + x1.x; sy = sy + y1.x; sx = sx + x1.y; sy = sy + y1.y; sx = sx + x1.z; sy = sy + y1.z; sx = sx + x1.w; sy = sy + y1.w;
+}
+__device__ __forceinline__ void x8_consume_round(const float* half, int lane, int j, int ntile, float& sx, float& sy) {
+  if ((j + 1) * KX_PROD <= ntile) {
+#pragma unroll
+    for (int w = 0; w < KX_PROD; ++w) x8_consume(half + w * X8_TILE, lane, w == 0 && j == 0, sx, sy);
+  } else {
+    for (int w = 0; j * KX_PROD + w < ntile; ++w) x8_consume(half + w * X8_TILE, lane, w == 0 && j == 0, sx, sy);
+  }
+}
+
+// producer: the six values of the lane's two pixels -> stage[k][c][2q], [2q+1]
+__device__ __forceinline__ void x8_store(float* tile, int q, int c, const float* v0, const float* v1) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    *reinterpret_cast<float2*>(tile + (k * 8 + c) * 8 + 2 * q) = make_float2(v0[k], v1[k]);
+}
+
+template <bool PN>
+__global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
+  constexpr int N = 64;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ KxShared S;
+  __shared__ int s_nv[8];
+
+  const int t = blockIdx.x + prm.t0;
+  const ict_optparam& op = prm.op;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t off = prm.pt_off[t];
+  const int n_in = (int)(prm.pt_off[t + 1] - off);
+  const int P = min(n_in, op.maxpttrack);
+  const bool donorm = op.donorm != 0;
+  const bool pnorm = PN && op.dopatchnorm != 0;
+  const int q2 = lane >> 3, cc = lane & 7;
+  const int ROUNDS = (P + KX_PROD - 1) / KX_PROD;
+
+  float2* s_ref2 = reinterpret_cast<float2*>(smem);    // [P][32]: (row 2q, row 2q+1) of column c, lane = 8q + c
+  float2* s_gx2 = s_ref2 + 32 * P;
+  float2* s_gy2 = s_gx2 + 32 * P;
+  float* s_ring = reinterpret_cast<float*>(s_gy2 + 32 * P);   // [2][KX_PROD][X8_TILE]
+  float4* s_rpl = reinterpret_cast<float4*>(s_ring + 2 * KX_PROD * X8_TILE);   // [P][2] reference placement
+  float4* s_npl = s_rpl + 2 * P;                        // [P][2] new-frame placement
+  float* s_AB = reinterpret_cast<float*>(s_npl + 2 * P);    // [P][12]
+  float* s_X = s_AB + 12 * P;
+  float* s_Y = s_X + P;
+  float* s_Z = s_Y + P;
+  float* s_Xc = s_Z + P;
+  float* s_Yc = s_Xc + P;
+  float* s_Zc = s_Yc + P;
+
+  const int rf = prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref;
+  const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
+  const FrameDesc* fr_ref = prm.frames + rf;
+  const FrameDesc* fr_new = prm.frames + nf;
+  const bool chainw = warp == KX_PROD;
+
+  // ---- ResetOdometer (odometer.cpp:580-609) + points -----------------------------------------------------------------
+  {
+    const float2 z2 = make_float2(0.f, 0.f);
+    for (int e = tid; e < 3 * 32 * P; e += nt) s_ref2[e] = z2;
+    const float* q = prm.pt3d + 3 * off;
+    for (int i = tid; i < P; i += nt) {
+      s_X[i] = q[i];
+      s_Y[i] = q[n_in + i];
+      s_Z[i] = q[2 * (int64_t)n_in + i];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s_AB[i * 12 + k] = 0.0f;
+    }
+  }
+  if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
+  if (tid >= 32 && tid < 34) {
+    mbar_init(&S.full[tid - 32], 32 * KX_PROD);
+    mbar_init(&S.empty[tid - 32], 32);
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += nt) {   // project_pt_save_rotated, pose.cpp:400-488
+    const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
+    const float xc = S.G[0] * X + S.G[1] * Y + S.G[2] * Z + S.G[3];
+    const float yc = S.G[4] * X + S.G[5] * Y + S.G[6] * Z + S.G[7];
+    const float zc = S.G[8] * X + S.G[9] * Y + S.G[10] * Z + S.G[11];
+    s_Xc[i] = xc;
+    s_Yc[i] = yc;
+    s_Zc[i] = zc;
+    if (prm.pt2d_out) {
+      const int l = op.lv_l;
+      prm.pt2d_out[2 * off + i] = (xc / zc) * prm.cam.fx[l] + prm.cam.cx[l];
+      prm.pt2d_out[2 * off + n_in + i] = (yc / zc) * prm.cam.fy[l] + prm.cam.cy[l];
+    }
+  }
+  __syncthreads();
+
+  float* trace = prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
+  int trace_n = 0;
+  float normdp_init = 1e-10f;
+  int nvsum = 0;
+  int ground = 0;                 // rounds done so far, counted alike by every warp: half = ground & 1, use = ground >> 1
+
+  for (int sl = op.lv_f; sl >= op.lv_l; --sl) {
+    const float fx = prm.cam.fx[sl], fy = prm.cam.fy[sl], cx = prm.cam.cx[sl], cy = prm.cam.cy[sl];
+    const float swo = prm.cam.swo[sl], sho = prm.cam.sho[sl];
+    const int width = prm.cam.width[sl];
+    const float* __restrict__ Iref = fr_ref->I[sl];
+    const float* __restrict__ Dxr = fr_ref->dx[sl];
+    const float* __restrict__ Dyr = fr_ref->dy[sl];
+    const float* __restrict__ Inew = fr_new->I[sl];
+
+    // ---- 4a. per point: reference placement + steepest-descent coefficients (odometer.cpp:268-279, 306-326) ------
+    for (int i = tid; i < P; i += nt) {
+      const float xc = s_Xc[i], yc = s_Yc[i], zc = s_Zc[i];
+      const float mx = (xc / zc) * fx + cx, my = (yc / zc) * fy + cy;
+      const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
+      PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
+      if (vis) {
+        pl = patch_place(mx, my, 4, width);
+        float c[10];
+        sd_coefs(xc, yc, zc, fx, fy, c);
+        float* ab = s_AB + i * 12;
+        ab[0] = c[0]; ab[1] = 0.0f; ab[2] = c[2]; ab[3] = c[4]; ab[4] = c[6]; ab[5] = c[8];
+        ab[6] = 0.0f; ab[7] = c[1]; ab[8] = c[3]; ab[9] = c[5]; ab[10] = c[7]; ab[11] = c[9];
+      }
+      s_rpl[2 * i] = make_float4(__int_as_float(pl.base), __int_as_float(vis), 0.0f, 0.0f);
+      s_rpl[2 * i + 1] = make_float4(pl.w0, pl.w1, pl.w2, pl.w3);
+    }
+    __syncthreads();
+    // ---- 4b. template gather (all eight warps; util_getPatch_grad, unfused, reference order) ------------------------
+    for (int i = warp; i < P; i += 8) {
+      const float4 pa = s_rpl[2 * i], pw = s_rpl[2 * i + 1];
+      if (__float_as_int(pa.y)) {
+        const int o = __float_as_int(pa.x) + (2 * q2 - 1) * width + cc;
+        const V8Rows ri = v8_load(Iref, o, width), rx = v8_load(Dxr, o, width), ry = v8_load(Dyr, o, width);
+        float2 r = v8_bilin_exact(ri, pw);
+        if (pnorm) {                     // utilities.cpp:187-188: tmp.sum() / novals, Eigen's order
+          const float m = x8_patch_sum(r.x, r.y) / N;
+          r.x = r.x - m;
+          r.y = r.y - m;
+        }
+        s_ref2[i * 32 + lane] = r;
+        s_gx2[i * 32 + lane] = v8_bilin_exact(rx, pw);
+        s_gy2[i * 32 + lane] = v8_bilin_exact(ry, pw);
+      }
+    }
+    __syncthreads();
+
+    // ---- 6. Hessian: 21 reference-order sums in four passes of six (odometer.cpp:428-472) --------------------------
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      if (!chainw) {
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1, use = ground >> 1;
+          if (use > 0) mbar_wait_relaxed(&S.empty[h], (use - 1) & 1);
+          const int i = j * KX_PROD + warp;
+          if (i < P) {
+            const float2 GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
+            float ab[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
+            float sd0[6], sd1[6], v0[6], v1[6];
+            kx_sd(GX.x, GY.x, ab, sd0);
+            kx_sd(GX.y, GY.y, ab, sd1);
+            switch (pass) {
+              case 0: kx_hess_products<0>(sd0, v0); kx_hess_products<0>(sd1, v1); break;
+              case 1: kx_hess_products<1>(sd0, v0); kx_hess_products<1>(sd1, v1); break;
+              case 2: kx_hess_products<2>(sd0, v0); kx_hess_products<2>(sd1, v1); break;
+              default: kx_hess_products<3>(sd0, v0); kx_hess_products<3>(sd1, v1); break;
+            }
+            x8_store(s_ring + (h * KX_PROD + warp) * X8_TILE, q2, cc, v0, v1);
+          }
+          mbar_arrive(&S.full[h]);
+          ++ground;
+        }
+      } else {
+        float sx = 0.0f, sy = 0.0f;
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1;
+          mbar_wait(&S.full[h], (ground >> 1) & 1);
+          x8_consume_round(s_ring + h * KX_PROD * X8_TILE, lane, j, P, sx, sy);
+          mbar_arrive(&S.empty[h]);
+          ++ground;
+        }
+        const float rx = kx_finish(sx), ry = kx_finish(sy);
+        if ((lane & 7) == 0) {
+          const int q = 6 * pass + (lane >> 3);
+          if (q < 21) S.Hsum[q] = rx;
+          if (lane < 16 && q + 4 < 21) S.Hsum[q + 4] = ry;
+        }
+      }
+    }
+    // ---- factorisation ---------------------------------------------------------------------------------------------------
+    if (chainw) {
+      __syncwarp();
+      lu6_factor_warp(S.Hsum, S.f);      // Eigen's fullPivLu, bit-identical
+      normdp_init = 1e-10f;              // odometer.cpp:341-342
+      if (lane == 0) {
+        S.it = 0;
+        S.cont = (0 < op.maxiter) & ((1e-10f / 1e-10f) > op.normdp_ratio);
+      }
+    }
+    __syncthreads();
+
+    // ---- iterations (odometer.cpp:344-419) ----------------------------------------------------------------------------
+    int it = 0;
+    while (S.cont) {
+      float sx = 0.0f, sy = 0.0f;
+      if (!chainw) {
+        // 7. project_pt + new-frame placement of this warp's patches (7m + warp), lanes = patches
+        {
+          const int i = lane * KX_PROD + warp;
+          int v = 0;
+          if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4);
+          const int nvw = __popc(__ballot_sync(0xffffffffu, v));
+          if (lane == 0) s_nv[warp] = nvw;
+        }
+        __syncwarp();
+        // 8. one patch per round; the new-frame rows of the NEXT patch are fetched one round ahead
+        V8Rows ln = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool lvis = false;
+        auto fetch = [&](int i) {
+          const float4 pa = s_npl[2 * i];
+          lw = s_npl[2 * i + 1];
+          lvis = __float_as_int(pa.y) != 0;
+          if (lvis) ln = v8_load(Inew, __float_as_int(pa.x) + (2 * q2 - 1) * width + cc, width);
+        };
+        if (warp < P) fetch(warp);
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int i = j * KX_PROD + warp;
+          const int h = ground & 1, use = ground >> 1;
+          const bool have = i < P;
+          float v0[6], v1[6];
+          if (have) {
+            const bool vis = lvis;
+            float2 pn = make_float2(0.f, 0.f);
+            if (vis) {
+              pn = v8_bilin_exact(ln, lw);           // util_getPatch (utilities.cpp:55-113), unfused
+              if (pnorm) {                           // utilities.cpp:111-112, Eigen's order
+                const float mn = x8_patch_sum(pn.x, pn.y) / N;
+                pn.x = pn.x - mn;
+                pn.y = pn.y - mn;
+              }
+            }
+            if (i + KX_PROD < P) fetch(i + KX_PROD);
+            const float2 R = s_ref2[i * 32 + lane], GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
+            float ab[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
+            float sd0[6], sd1[6];
+            kx_sd(GX.x, GY.x, ab, sd0);
+            kx_sd(GX.y, GY.y, ab, sd1);
+            const float p0 = vis ? R.x - pn.x : 0.0f, p1 = vis ? R.y - pn.y : 0.0f;   // pdiff, odometer.cpp:381
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { v0[k] = sd0[k] * p0; v1[k] = sd1[k] * p1; }   // sd_k_proj, :386-391
+          }
+          if (use > 0) mbar_wait_relaxed(&S.empty[h], (use - 1) & 1);
+          if (have) x8_store(s_ring + (h * KX_PROD + warp) * X8_TILE, q2, cc, v0, v1);
+          mbar_arrive(&S.full[h]);
+          ++ground;
+        }
+      } else {
+        for (int j = 0; j < ROUNDS; ++j) {
+          const int h = ground & 1;
+          mbar_wait(&S.full[h], (ground >> 1) & 1);
+          x8_consume_round(s_ring + h * KX_PROD * X8_TILE, lane, j, P, sx, sy);
+          mbar_arrive(&S.empty[h]);
+          ++ground;
+        }
+        // 9a. sumsd[k]: Eigen's redux of the eight chains
+        const float rx = kx_finish(sx), ry = kx_finish(sy);
+        if ((lane & 7) == 0) {
+          S.sum[lane >> 3] = rx;
+          if (lane < 16) S.sum[4 + (lane >> 3)] = ry;
+        }
+        __syncwarp();
+        int nv = 0;
+        if (lane == 0) {
+          for (int w = 0; w < KX_PROD; ++w) nv += s_nv[w];
+          float sumsd[6], dp[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sumsd[k] = S.sum[k];
+          lu6_solve_exact(S.f, S.sum, S.dp);                     // 9b. odometer.cpp:407, Eigen's substitution order
+          float pr[6], Gr[12];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { dp[k] = S.dp[k]; pr[k] = S.p[k] + dp[k]; S.p[k] = pr[k]; }   // 10. addpose_se3
+          Gr[3] = Gr[7] = Gr[11] = 0.0f;
+          se3_exp<float>(Gr, pr);
+#pragma unroll
+          for (int k = 0; k < 12; ++k) S.G[k] = Gr[k];
+          const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
+                               (fabsf(dp[4]) + fabsf(dp[5]));           // lpNorm<1>, odometer.cpp:412
+          S.dp[6] = normdp;
+          S.nv = nv;
+          if (trace && trace_n < prm.trace_cap) {
+            float* rec = trace + (int64_t)ICT_TRACE_FLOATS * trace_n;
+            rec[0] = (float)sl;
+            rec[1] = (float)it;
+            for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+            rec[14] = normdp;
+            rec[15] = (float)nv;
+            for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+          }
+        }
+        __syncwarp();
+        if (trace && trace_n < prm.trace_cap) ++trace_n;
+        const float normdp = S.dp[6];
+        nvsum += S.nv;
+        if (it == 0) normdp_init = normdp;
+        const int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
+        if (lane == 0) {
+          S.it = it + 1;
+          S.cont = cont;
+        }
+      }
+      __syncthreads();
+      ++it;
+    }
+    if (chainw && lane == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
+  }
+
+  if (chainw && lane == 0) {
+    getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
+                prm.p_out + 6 * (int64_t)t);
+    if (prm.npixres) prm.npixres[t] = (long long)nvsum * N;
+    if (trace)
+      for (int k = trace_n; k < prm.trace_cap; ++k) {
+        float* rec = trace + (int64_t)ICT_TRACE_FLOATS * k;
+        for (int j = 0; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
+        rec[0] = -1.0f;
+      }
+  }
+}
+
+size_t kx8_smem_bytes(const ict_optparam& op, int max_pts) {
+  const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
+  return sizeof(float) * (3 * 64 * P + 2 * KX_PROD * X8_TILE + 36 * P);
+}
+
+bool kx8_supported(const ict_optparam& op, int max_pts) {
+  const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
+  return op.psz == 8 && P <= KX_PROD * X8_MAXR && kx8_smem_bytes(op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT;
+}
+
+template <bool PN>
+static cudaError_t launch_x8_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
+  static bool attr_dev[64] = {};            // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_dev[dev_ & 63];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_track_x8<PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x8<PN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_track_x8<PN><<<prm.T, 256, smem, stream>>>(prm);
+  count_launch_external();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t stream) {
+  if (prm.T <= 0) return cudaSuccess;
+  const size_t smem = kx8_smem_bytes(prm.op, max_pts);
+  return prm.op.dopatchnorm ? launch_x8_t<true>(prm, smem, stream) : launch_x8_t<false>(prm, smem, stream);
+}
+
+}  // namespace ict

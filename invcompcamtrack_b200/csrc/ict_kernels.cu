@@ -1255,6 +1255,8 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
       default: return launch_track_fast_t<32>(prm, fsm, nt, stream);
     }
   }
+  if ((mode & 2) && !prm.force_general && !getenv("ICT_EXACT_V1") && kx8_supported(prm.op, max_pts))
+    return launch_track_x8(prm, max_pts, stream);      // K2x8: reference-order sums, 8x8 patches, +/- dopatchnorm
   if (mode == 2 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_EXACT_V1") &&
       kx_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
     return launch_track_x(prm, max_pts, stream);       // K2x: reference-order sums, producer/chain warps

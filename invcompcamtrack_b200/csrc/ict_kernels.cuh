@@ -81,6 +81,12 @@ cudaError_t launch_track_v8(const TrackParams& prm, int max_pts, cudaStream_t st
 size_t kx_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_x(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
+// K2x8 (ict_kernel_x8.cu): reference-order sums for 8x8 patches (up to 224 points per track), with or without
+// dopatchnorm — bit-identical to the oracle like k_track<8,2|3>.
+bool kx8_supported(const ict_optparam& op, int max_pts);
+size_t kx8_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
 // K2p: two track slots per persistent CTA, serial steps of one slot overlapped with pixel steps of the other.
 // ticket: one device int (zeroed by the launch).  Handles psz 8/16/32 without dopatchnorm, tree sums.
 size_t pipe_smem_bytes(const ict_optparam& op, int max_pts);

@@ -13,6 +13,7 @@ op_c = O.make_optparam(lv_f=3, lv_l=0, psz=8, maxiter=10, normdp_ratio=0.01, don
 op = ict.OptParam.from_buffer_copy(bytes(op_c))
 fr = ict.Frames(NF, 640, 480, 3, 8); fr.upload(0, np.stack(frames))
 tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+tr.set_sum_order(int(os.environ.get('SUM_ORDER', 0)))
 pts = np.concatenate([sc.points(100 + s, 100, 8, 3) for s in range(S)])
 tr.set_points(np.arange(S + 1, dtype=np.int64) * 100, pts)
 for rep in range(3):
