@@ -314,6 +314,8 @@ CASES8 = [
     dict(seed=76, npts=50, scale=3.0, ntracks=6),            # large motion
     dict(seed=77, npts=60, donorm=1, dopatchnorm=1, ntracks=4),   # the MATLAB harness's settings
     dict(seed=78, npts=33, dopatchnorm=1, lv_f=2, lv_l=1, maxiter=3, ratio=0.1, ntracks=3),
+    dict(seed=79, npts=200, dopatchnorm=1, ntracks=2),       # 29 rounds of seven patches, 202 KB of shared memory
+    dict(seed=80, npts=230, ntracks=1),                      # beyond one CTA in the reference order: multi-CTA path
 ]
 
 
@@ -321,6 +323,9 @@ CASES8 = [
 def test_psz8_kernel_edge_cases(ict, orc, kw):
     case = make_case(psz=8, **kw)
     o = oracle_run(orc, case, trace_cap=48)
+    gx = gpu_run(ict, case, trace_cap=48, sum_order=1)       # K2x8 (k_track<8,2|3> beyond 224 points): bit for bit
+    assert np.array_equal(gx["pt2d"], o["pt2d"])
+    assert_bit_identical(gx, o)
     g = gpu_run(ict, case, trace_cap=48)
     assert np.array_equal(g["pt2d"], o["pt2d"])
     res = check_parity(g, o, case, gates=False)
@@ -344,6 +349,7 @@ def test_psz8_kernel_points_out_of_view(ict, orc):
     p_in[:, 4] = 0.02
     o = oracle_run(orc, case, trace_cap=48, p_in=p_in)
     assert (o["trace"][:, 0, 15] < 40).any() and (o["trace"][:, 0, 15] > 0).any()
+    assert_bit_identical(gpu_run(ict, case, trace_cap=48, sum_order=1, p_in=p_in), o)
     g = gpu_run(ict, case, trace_cap=48, p_in=p_in)
     res = check_parity(g, o, case, gates=False)
     assert res["jtr_first"] <= 1e-5, res
