@@ -400,3 +400,54 @@ def test_full_size_batch_properties(ict, orc):
     assert np.array_equal(xs["p_out"][sub], x["p_out"])
     assert np.median(np.abs(a["p_out"][sub] - o["p_out"]).max(axis=1)) < 1e-4   # default order: same poses in the median
     fr.close()
+
+
+def test_stream_entry_points_equal_blocking_ones(ict):
+    """ict_frames_upload_u8_stream / ict_tracker_set_points_stream / ict_track_batch_stream (pinned host buffers,
+    copies on internal lanes, kernels on the caller's stream) give the results of the blocking entry points, chunk by
+    chunk and across repeated steps that reuse the staging areas."""
+    import ctypes as C
+    import torch
+    case = make_case(seed=95, w=1280, h=704, psz=32, npts=4, ntracks=600)
+    T, P, L = case["T"], case["npts"], case["lv_f"] + 1
+    op = ict.OptParam.from_buffer_copy(bytes(case["op"]))
+    frames_u8 = np.stack([case["A"], case["B"]]).astype(np.uint8)
+    fr = ict.Frames(2, case["w"], case["h"], case["lv_f"], case["psz"])
+    fr.upload(0, frames_u8.astype(np.float32))
+    tr = ict.Tracker(op, case["sc"].fc, case["sc"].cc, case["sc"].wh)
+    tr.set_points(case["pt_off"], case["pts"].copy())
+    ref = tr.track_batch(fr, 0, 1, np.zeros((T, 6)))
+    tr.close()
+    lib, v = ict.lib(), C.c_void_p
+    st = torch.cuda.Stream()
+    h_frames = torch.from_numpy(frames_u8).pin_memory()
+    h_pts = torch.from_numpy(case["pts"].copy()).pin_memory()
+    h_ref = torch.zeros(T, dtype=torch.int32).pin_memory()
+    h_new = torch.ones(T, dtype=torch.int32).pin_memory()
+    h_pin = torch.zeros(T, 6, dtype=torch.float64).pin_memory()
+    h_pout = torch.zeros(T, 6, dtype=torch.float64).pin_memory()
+    h_iters = torch.zeros(T, L, dtype=torch.int32).pin_memory()
+    h_npix = torch.zeros(T, dtype=torch.int64).pin_memory()
+    bounds = [0, 250, 600]
+    fr2 = ict.Frames(2, case["w"], case["h"], case["lv_f"], case["psz"])
+    trk = [ict.Tracker(op, case["sc"].fc, case["sc"].cc, case["sc"].wh) for _ in range(2)]
+    offs = [torch.from_numpy(np.arange(bounds[c + 1] - bounds[c] + 1, dtype=np.int64) * P).pin_memory() for c in range(2)]
+    for step in range(3):
+        h_pout.zero_()
+        for c in range(2):
+            t0, t1 = bounds[c], bounds[c + 1]
+            rc = lib.ict_frames_upload_u8_stream(fr2.h_, 0, 2, v(h_frames.data_ptr()), v(st.cuda_stream))
+            rc |= lib.ict_tracker_set_points_stream(trk[c].h_, t1 - t0, v(offs[c].data_ptr()),
+                                                    v(h_pts.data_ptr() + 8 * 3 * P * t0), v(st.cuda_stream))
+            rc |= lib.ict_track_batch_stream(trk[c].h_, fr2.h_, v(h_ref.data_ptr() + 4 * t0), v(h_new.data_ptr() + 4 * t0),
+                                             v(h_pin.data_ptr() + 48 * t0), v(h_pout.data_ptr() + 48 * t0),
+                                             v(h_iters.data_ptr() + 4 * L * t0), v(h_npix.data_ptr() + 8 * t0),
+                                             v(st.cuda_stream))
+            assert rc == 0, lib.ict_last_error()
+        st.synchronize()
+        assert np.array_equal(h_pout.numpy(), ref["p_out"]), step
+        assert np.array_equal(h_iters.numpy(), ref["iters"]) and np.array_equal(h_npix.numpy(), ref["npixres"])
+    for t_ in trk:
+        t_.close()
+    fr.close()
+    fr2.close()
