@@ -38,8 +38,8 @@ namespace ict {
 
 void count_launch_external();
 
-template <int KT, int MINB, bool TRACE>
-__global__ void __launch_bounds__(256, MINB) k_track_v2(const TrackParams prm) {
+template <int KT, int MINB, bool TRACE, int NT>
+__global__ void __launch_bounds__(NT, MINB) k_track_v2(const TrackParams prm) {
   constexpr int N = 1024;                 // pixels per patch (psz 32)
   constexpr int GPP = 32 / KT;            // groups (KT rows, lane = column) per point
   constexpr int RQ = KT / 4;              // float4 row-quads per group
@@ -406,23 +406,23 @@ size_t v2_smem_bytes(const ict_optparam& op, int max_pts) {
   return sizeof(float) * (3 * P * 1024 + 72 * P);
 }
 
-template <int KT, int MINB, bool TRACE>
+template <int KT, int MINB, bool TRACE, int NT = 256>
 static cudaError_t launch_v2_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
   static bool attr_dev[64] = {};            // function attributes are per device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
     const char* co = getenv("ICT_V2_CARVEOUT");      // profiling knob: shared-memory carve-out in percent
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                co ? atoi(co) : 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_track_v2<KT, MINB, TRACE><<<prm.T, 256, smem, stream>>>(prm);
+  k_track_v2<KT, MINB, TRACE, NT><<<prm.T, NT, smem, stream>>>(prm);
   count_launch_external();
   return cudaGetLastError();
 }
@@ -436,6 +436,13 @@ cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t st
     const char* e = getenv("ICT_V2_VARIANT");       // tuning knob for profiling runs only
     variant = e ? atoi(e) : 0;
   }
+  // More points per track = more template per CTA = fewer CTAs per SM: keep ~32 warps per SM by giving the track more
+  // warps (a warp still owns 16 rows of one point at a time; per-group sums make the result independent of it).
+  const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
+  if (P > 8 && !getenv("ICT_V2_256"))
+    return prm.trace ? launch_v2_t<16, 1, true, 1024>(prm, smem, stream) : launch_v2_t<16, 1, false, 1024>(prm, smem, stream);
+  if (P > 4 && !getenv("ICT_V2_256"))
+    return prm.trace ? launch_v2_t<16, 2, true, 512>(prm, smem, stream) : launch_v2_t<16, 2, false, 512>(prm, smem, stream);
   if (prm.trace) return launch_v2_t<16, 4, true>(prm, smem, stream);   // same arithmetic + per-iteration records
   switch (variant) {
     case 1: return launch_v2_t<8, 4, false>(prm, smem, stream);
