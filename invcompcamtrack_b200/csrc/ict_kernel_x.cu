@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
   float4* s_gy4 = s_gx4 + E / 4;
   float4* s_ring = s_gy4 + E / 4;                            // [2][KX_PROD] tiles of KX_TILE_F4 float4
   float4* s_rpl = s_ring + 2 * KX_PROD * KX_TILE_F4;         // [P][2] reference placement {base,vis,-,-},{w0..w3}
-  float4* s_npl = s_rpl + 2 * P;                             // [P][2] new-frame placement of the coming iteration
-  float* s_AB = reinterpret_cast<float*>(s_npl + 2 * P);     // [P][12]
+  float4* s_npl = s_rpl + 2 * P;                             // [KX_PROD][P][2] new-frame placement, one copy per producer
+  float* s_AB = reinterpret_cast<float*>(s_npl + 2 * P * KX_PROD);   // [P][12]
   float* s_X = s_AB + 12 * P;
   float* s_Y = s_X + P;
   float* s_Z = s_Y + P;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
   float* trace = prm.trace ? prm.trace + (int64_t)t * prm.trace_cap * ICT_TRACE_FLOATS : nullptr;
   int trace_n = 0;
   float normdp_init = 1e-10f;
-  int nv = 0, nvsum = 0;          // chain warp only
+  int nvsum = 0;                  // chain warp only
   int ground = 0;                 // rounds done so far, counted alike by every warp: half = ground & 1, use = ground >> 1
   const int ROUNDS = (NTILE + KX_PROD - 1) / KX_PROD;
 
@@ -252,17 +252,10 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
         }
       }
     }
-    // ---- factorisation, first placement ---------------------------------------------------------------------------------
+    // ---- factorisation ---------------------------------------------------------------------------------------------------
     if (chainw) {
       __syncwarp();
       lu6_factor_warp(S.Hsum, S.f);      // Eigen's fullPivLu, bit-identical
-      nv = 0;
-      for (int i0 = 0; i0 < P; i0 += 32) {
-        const int i = i0 + lane;
-        int v = 0;
-        if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i);
-        nv += __popc(__ballot_sync(0xffffffffu, v));
-      }
       normdp_init = 1e-10f;              // odometer.cpp:341-342
       if (lane == 0) {
         S.it = 0;
@@ -276,6 +269,21 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     while (S.cont) {
       float sx = 0.0f, sy = 0.0f;
       if (!chainw) {
+        // 7. project_pt + new-frame placement (pose.cpp:307-397, utilities.cpp:65-94), lanes = points.  Every
+        // producer computes it for itself into its own copy: the chain warp — the critical resource — is spared the
+        // ~130 instructions and the producers have the slack.
+        float4* npl = s_npl + warp * 2 * P;
+        {
+          int nvw = 0;
+          for (int i0 = 0; i0 < P; i0 += 32) {
+            const int i = i0 + lane;
+            int v = 0;
+            if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, npl + 2 * i);
+            nvw += __popc(__ballot_sync(0xffffffffu, v));
+          }
+          if (warp == 0 && lane == 0) S.nv = nvw;
+        }
+        __syncwarp();
         // producer state: the new-frame rows of the NEXT tile, fetched one tile ahead so that the L2 round trip is
         // covered by the current tile's arithmetic
         float la[5], lb[5];
@@ -285,8 +293,8 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
         for (int r = 0; r < 5; ++r) la[r] = lb[r] = 0.0f;
         auto fetch = [&](int tl) {
           const int i = tl >> 3, rq = tl & 7;
-          const float4 pa = s_npl[2 * i];
-          lw = s_npl[2 * i + 1];
+          const float4 pa = npl[2 * i];
+          lw = npl[2 * i + 1];
           lvis = __float_as_int(pa.y) != 0;
           if (lvis) {
             const float* pI = Inew + (__float_as_int(pa.x) + (rq * 4 - 1) * width + lane);
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
             rec[1] = (float)it;
             for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
             rec[14] = normdp;
-            rec[15] = (float)nv;
+            rec[15] = (float)S.nv;
             for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
           }
         }
@@ -370,19 +378,10 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
         const float normdp = S.dp[6];
         if (it == 0) normdp_init = normdp;
         const int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
-        nvsum += nv;
+        nvsum += S.nv;
         if (lane == 0) {
           S.it = it + 1;
           S.cont = cont;
-        }
-        if (cont) {                      // 7. project_pt with the new pose + placement for the next iteration
-          nv = 0;
-          for (int i0 = 0; i0 < P; i0 += 32) {
-            const int i = i0 + lane;
-            int v = 0;
-            if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i);
-            nv += __popc(__ballot_sync(0xffffffffu, v));
-          }
         }
       }
       __syncthreads();
@@ -406,7 +405,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
 
 size_t kx_smem_bytes(const ict_optparam& op, int max_pts) {
   const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
-  return sizeof(float) * (3 * P * 1024 + 2 * KX_PROD * KX_TILE_F4 * 4 + 40 * P);
+  return sizeof(float) * (3 * P * 1024 + 2 * KX_PROD * KX_TILE_F4 * 4 + (32 + 8 * KX_PROD) * P);
 }
 
 cudaError_t launch_track_x(const TrackParams& prm, int max_pts, cudaStream_t stream) {
