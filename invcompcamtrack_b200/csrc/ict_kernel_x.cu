@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
     int it = 0;
     while (S.cont) {
       float sx = 0.0f, sy = 0.0f;
+      long long t_c0 = 0, t_c1 = 0;       // instrumentation (trace records [22], [23]): chain loop, serial section
       if (!chainw) {
         // 7. project_pt + new-frame placement (pose.cpp:307-397, utilities.cpp:65-94), lanes = points.  Every
         // producer computes it for itself into its own copy: the chain warp — the critical resource — is spared the
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
           ++ground;
         }
       } else {
+        t_c0 = trace ? clock64() : 0;
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
           mbar_wait(&S.full[h], (ground >> 1) & 1);
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
+        t_c1 = trace ? clock64() : 0;
       }
 
       if (chainw) {
@@ -371,6 +374,8 @@ __global__ void __launch_bounds__(256, 2) k_track_x(const TrackParams prm) {
             rec[14] = normdp;
             rec[15] = (float)S.nv;
             for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+            rec[22] = (float)(clock64() - t_c1);   // cycles of the serial section (finish, solve, exp)
+            rec[23] = (float)(t_c1 - t_c0);        // cycles the chain warp spent consuming the rounds of this sum
           }
         }
         __syncwarp();

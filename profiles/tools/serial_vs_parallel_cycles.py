@@ -4,7 +4,7 @@ import numpy as np
 import invcompcamtrack_b200 as ict
 from helpers import make_case, gpu_run
 case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=4096)
-g = gpu_run(ict, case, trace_cap=48)
+g = gpu_run(ict, case, trace_cap=48, sum_order=int(os.environ.get('SUM_ORDER', '0')))
 tr = g["trace"]; m = tr[...,0] >= 0
 m0 = m & (tr[...,1] == 0)
 print("level setup (Hessian sums + LU factor) cycles: median %.0f mean %.0f" % (np.median(tr[...,21][m0]), tr[...,21][m0].mean()))
