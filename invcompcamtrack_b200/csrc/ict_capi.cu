@@ -539,7 +539,6 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.dbg_skip_serial = getenv("ICT_DBG_SKIP_SERIAL") ? atoi(getenv("ICT_DBG_SKIP_SERIAL")) : 0;
   prm.serial_warp_last = getenv("ICT_SERIAL_WARP_LAST") ? 1 : 0;
   prm.v2_lu_setup = getenv("ICT_V2_LU") ? 1 : 0;
-  const size_t smem = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode);
   // K2p (two slots per persistent CTA, ict_kernel_pipe.cu) measured 2.67e11 against 3.2e11 pixel-residuals/s for one
   // track per CTA on B200; it stays selectable for experiments and is covered by a parity test.
   const int use_pipe = getenv("ICT_PIPE") ? 1 : 0;
@@ -549,7 +548,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   if (pipe_ok) {
     CU(tr->ticket.reserve(sizeof(int)));
     CU(launch_track_pipe(prm, tr->max_pts, tr->ticket.as<int>(), st));
-  } else if (smem <= (size_t)ICT_TRACK_SMEM_LIMIT) {
+  } else if (track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general)) {
     CU(launch_track(prm, tr->max_pts, st));
   } else {
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
@@ -593,7 +592,7 @@ int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame,
   CU(cudaMemcpyAsync(tr->rf.p, ref_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
   CU(cudaMemcpyAsync(tr->nf.p, new_frame, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, 0));
   CU(cudaMemcpyAsync(tr->p_in.p, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
-  const bool big = track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode) > (size_t)ICT_TRACK_SMEM_LIMIT;
+  const bool big = !track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general);
   int rc;
   if (big) {
     // multi-CTA path runs one track at a time with fixed frames
@@ -623,7 +622,7 @@ int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref
   cudaStream_t st = (cudaStream_t)stream;
   const int T = tr->T;
   if (T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
-  if (track_smem_bytes(tr->op, tr->max_pts, tr->sum_mode) > (size_t)ICT_TRACK_SMEM_LIMIT)
+  if (!track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general))
     return fail(ICT_ERR_UNSUPPORTED, "stream variant handles tracks that fit one CTA");
   const int L = tr->op.lv_f - tr->op.lv_l + 1;
   CU(tr->rf.reserve(sizeof(int) * (size_t)T));

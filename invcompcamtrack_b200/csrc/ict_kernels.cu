@@ -1233,10 +1233,19 @@ static cudaError_t launch_track_p(const TrackParams& prm, size_t smem, int nt, i
   }
 }
 
+// True when one CTA can hold a whole track: the general kernel's layout fits, or one of the patch-size-8 kernels
+// (denser layouts: no fourth plane for dopatchnorm) takes the configuration.  Otherwise the multi-CTA path runs.
+bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int force_general) {
+  if (track_smem_bytes(op, max_pts, sum_mode) <= (size_t)ICT_TRACK_SMEM_LIMIT) return true;
+  if (force_general) return false;
+  if (sum_mode) return !getenv("ICT_EXACT_V1") && kx8_supported(op, max_pts);
+  return !getenv("ICT_FAST_V1") && v8_supported(op, max_pts);
+}
+
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
   const size_t smem = track_smem_bytes(prm.op, max_pts, prm.sum_mode);
-  if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
+  if (!track_fits_one_cta(prm.op, max_pts, prm.sum_mode, prm.force_general)) return cudaErrorInvalidConfiguration;
   const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
   const long long E = (long long)P * prm.op.novals;
   int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);

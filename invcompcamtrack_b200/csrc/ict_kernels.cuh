@@ -62,6 +62,7 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 // a6..a18: SetPose + TrackPose, one CTA per track, template + gradients resident in shared memory.
 // Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
+bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int force_general);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
 // K2v2 (ict_kernel_v2.cu): the production kernel for psz 32 without dopatchnorm, tree sums; launch_track routes

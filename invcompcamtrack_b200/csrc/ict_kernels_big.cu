@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(256) k_big_level_gather(const BigArgs a, int s
   }
 }
 
-// mean subtraction of each visible patch of buf: one warp per patch, fixed order
-__global__ void k_big_patch_means(const BigArgs a, float* buf, int visbit, int subtract) {
+// mean subtraction of each visible patch of buf: one warp per patch, fixed order (a warp tree; with exact != 0 the
+// reference's order, tmp.sum() of utilities.cpp:112, summed by one lane)
+__global__ void k_big_patch_means(const BigArgs a, float* buf, int visbit, int subtract, int exact) {
   const int n = a.prm.op.novals;
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -219,8 +220,13 @@ __global__ void k_big_patch_means(const BigArgs a, float* buf, int visbit, int s
   for (long long i = wid; i < a.P; i += nwarps) {
     if (!(a.w.vis[i] & visbit)) continue;
     float s = 0.0f;
-    for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
-    s = warp_sum(s);
+    if (exact) {
+      const float* b = buf + i * n;
+      if (lane == 0) s = eigen_sum_serial([&](int e) { return b[e]; }, n);
+    } else {
+      for (int k = lane; k < n; k += 32) s = s + buf[i * n + k];
+      s = warp_sum(s);
+    }
     s = __shfl_sync(0xffffffffu, s, 0);
     const float m = s / n;
     if (lane == 0) a.w.mean[i] = m;
@@ -773,7 +779,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const int ncta = a.w.ncta;
   const int pcta = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
   const bool pn = op.dopatchnorm != 0;
-  const bool ex = prm.sum_mode != 0;   // reference-order sums (patch means stay warp trees here)
+  const bool ex = prm.sum_mode != 0;   // reference-order sums
   const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !getenv("ICT_DENSE_V1");
   int nl = 0;
   k_big_init<<<ncta, 256, 0, st>>>(a); ++nl;
@@ -792,7 +798,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   for (int sl = op.lv_f; sl >= op.lv_l && !fused; --sl) {
     k_big_level_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
     k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
-    if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1); ++nl; }
+    if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1, ex ? 1 : 0); ++nl; }
     if (ex) {
       k_big_level_hessian_exact<<<1, 192, 0, st>>>(a); ++nl;
     } else {
@@ -803,7 +809,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
       k_big_iter_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
       if (pn) {
         k_big_iter_sample<<<ncta, 256, 0, st>>>(a, sl); ++nl;
-        k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.pnew, 2, 1); ++nl;
+        k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.pnew, 2, 1, ex ? 1 : 0); ++nl;
       }
       if (ex) {
         if (pn) k_big_iter_pdiff<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_pdiff<false><<<ncta, 256, 0, st>>>(a, sl);

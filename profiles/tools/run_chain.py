@@ -7,15 +7,16 @@ import invcompcamtrack_b200 as ict
 from invcompcamtrack_b200 import synth
 from oracle import oracle as O
 NF, S = int(os.environ.get("FRAMES", 100)), int(os.environ.get("SAMPLES", 1))
+NP = int(os.environ.get("NPTS", 100))
 sc, frames, poses = synth.make_sequence(5, NF, 640, 480)
 op_c = O.make_optparam(lv_f=3, lv_l=0, psz=8, maxiter=10, normdp_ratio=0.01, donorm=int(os.environ.get('DONORM', 0)),
-                        dopatchnorm=int(os.environ.get('PATCHNORM', 0)), maxpttrack=100)
+                        dopatchnorm=int(os.environ.get('PATCHNORM', 0)), maxpttrack=NP)
 op = ict.OptParam.from_buffer_copy(bytes(op_c))
 fr = ict.Frames(NF, 640, 480, 3, 8); fr.upload(0, np.stack(frames))
 tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
 tr.set_sum_order(int(os.environ.get('SUM_ORDER', 0)))
-pts = np.concatenate([sc.points(100 + s, 100, 8, 3) for s in range(S)])
-tr.set_points(np.arange(S + 1, dtype=np.int64) * 100, pts)
+pts = np.concatenate([sc.points(100 + s, NP, 8, 3) for s in range(S)])
+tr.set_points(np.arange(S + 1, dtype=np.int64) * NP, pts)
 for rep in range(3):
     t0 = time.perf_counter()
     out = tr.track_sequence(fr, 0, NF - 1, 1, np.zeros((S, 6)))

@@ -184,7 +184,8 @@ def test_sequence_chain(ict, orc):
 
 @pytest.mark.parametrize("kw", [dict(seed=61, w=320, h=240, lv_f=2, psz=1, dense_border=8, tilt=(0.15, -0.1)),
                                 dict(seed=62, w=320, h=240, lv_f=2, psz=1, dense_border=6, tilt=(0.1, 0.2), donorm=1),
-                                dict(seed=63, w=160, h=120, lv_f=1, psz=8, npts=900)])
+                                dict(seed=63, w=160, h=120, lv_f=1, psz=8, npts=900),
+                                dict(seed=64, w=160, h=120, lv_f=1, psz=8, npts=700, donorm=1, dopatchnorm=1)])
 def test_dense_alignment_multi_cta_path(ict, orc, kw):
     """BASELINE config 4 geometry (reduced): one track with one point per pixel and per-pixel depth, psz = 1 — too
     large for a CTA, so the multi-CTA path runs.  Bit-exact against the oracle in reference order; within fp32
@@ -304,18 +305,20 @@ def test_psz32_kernels_points_out_of_view(ict, orc):
     assert np.array_equal(g["trace"][:, 0, 15], o["trace"][:, 0, 15])
 
 
-# psz 8 in the default order runs K2v8 (up to 128 points per track, with or without dopatchnorm)
+# psz 8 in the default order runs K2v8 (8 warps up to 128 points per track, 16 warps up to 240; with or without
+# dopatchnorm)
 CASES8 = [
     dict(seed=71, npts=1),                                   # one point: rank-deficient H, Eigen's truncated solve
     dict(seed=72, npts=13, ntracks=5),                       # warps with one and with two points
     dict(seed=73, npts=128, ntracks=2),                      # all sixteen point slots of every warp
-    dict(seed=74, npts=130, ntracks=2),                      # beyond K2v8's limit: k_track_fast takes over
+    dict(seed=74, npts=130, ntracks=2),                      # K2v8 with sixteen warps, nine point slots each
     dict(seed=75, npts=90, maxpttrack=40, ntracks=2),        # more points than maxpttrack
     dict(seed=76, npts=50, scale=3.0, ntracks=6),            # large motion
     dict(seed=77, npts=60, donorm=1, dopatchnorm=1, ntracks=4),   # the MATLAB harness's settings
     dict(seed=78, npts=33, dopatchnorm=1, lv_f=2, lv_l=1, maxiter=3, ratio=0.1, ntracks=3),
     dict(seed=79, npts=200, dopatchnorm=1, ntracks=2),       # 29 rounds of seven patches, 202 KB of shared memory
     dict(seed=80, npts=230, ntracks=1),                      # beyond one CTA in the reference order: multi-CTA path
+    dict(seed=81, npts=240, donorm=1, dopatchnorm=1, ntracks=1),   # K2v8's largest track (223 KB of shared memory)
 ]
 
 
