@@ -113,9 +113,23 @@ template <int NV>
 __device__ __forceinline__ void finish_partials(const float* part, int ncta, float* out /*shared, NV*/) {
   __shared__ float s_p[8 * 21];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // a thread's first three CTAs are loaded before the first addition: one L2 round trip for the usual grid
+  // (at most 592 CTAs), not one per value
+  const int c0 = threadIdx.x, c1 = c0 + blockDim.x, c2 = c1 + blockDim.x;
+  float v0[NV], v1[NV], v2[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v0[k] = c0 < ncta ? __ldcg(part + c0 * 21 + k) : 0.0f;
+    v1[k] = c1 < ncta ? __ldcg(part + c1 * 21 + k) : 0.0f;
+    v2[k] = c2 < ncta ? __ldcg(part + c2 * 21 + k) : 0.0f;
+  }
+#pragma unroll
   for (int k = 0; k < NV; ++k) {
     float s = 0.0f;
-    for (int c = threadIdx.x; c < ncta; c += blockDim.x) s = s + part[c * 21 + k];
+    if (c0 < ncta) s = s + v0[k];
+    if (c1 < ncta) s = s + v1[k];
+    if (c2 < ncta) s = s + v2[k];
+    for (int c = c2 + blockDim.x; c < ncta; c += blockDim.x) s = s + __ldcg(part + c * 21 + k);
     s = warp_sum(s);
     if (lane == 0) s_p[warp * 21 + k] = s;
   }
@@ -128,13 +142,17 @@ __device__ __forceinline__ void finish_partials(const float* part, int ncta, flo
   __syncthreads();
 }
 
-__global__ void k_big_init(const BigArgs a) {
-  // ResetOdometer for the element/point state + setpose_se3
+__global__ void k_big_init(const BigArgs a, int fused) {
+  // ResetOdometer for the element/point state + setpose_se3.  The fused dense path keeps (ref, sd1..6) only.
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
-  for (long long e = gid; e < a.E; e += gsz) { a.w.ref[e] = 0.0f; a.w.gx[e] = 0.0f; a.w.gy[e] = 0.0f; }
+  for (long long e = gid; e < a.E; e += gsz) {
+    a.w.ref[e] = 0.0f;
+    if (!fused) { a.w.gx[e] = 0.0f; a.w.gy[e] = 0.0f; }
+  }
+  const int ncoef = fused ? 6 : 10;
   for (long long i = gid; i < a.P; i += gsz) {
-    a.w.vis[i] = 0;
-    for (int k = 0; k < 10; ++k) a.w.coef[(long long)k * a.P + i] = 0.0f;
+    if (!fused) a.w.vis[i] = 0;
+    for (int k = 0; k < ncoef; ++k) a.w.coef[(long long)k * a.P + i] = 0.0f;
   }
   if (gid == 0) {
     BigState* S = a.w.st;
@@ -478,7 +496,7 @@ __global__ void __launch_bounds__(64) k_big_iter_sums_exact(const BigArgs a) {
 // the pose and evaluates the stop rule.  Same per-element arithmetic, same thread partition and same summation order
 // as k_big_iter_points/elems/finish: results are bit-identical to that path (tests/test_gpu_parity.py).
 // ==================================================================================================
-__global__ void __launch_bounds__(256) k_dense_level(const BigArgs a, int sl) {
+__global__ void __launch_bounds__(256, 4) k_dense_level(const BigArgs a, int sl) {   // 592 CTAs = one resident wave
   const CamLevels& cam = a.prm.cam;
   const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
   const int width = cam.width[sl];
@@ -522,24 +540,25 @@ __global__ void __launch_bounds__(256) k_dense_level(const BigArgs a, int sl) {
 
 // Shared tail of the dense iteration kernels: CTA partial sums, visible-point count, ticket; the CTA that arrives last
 // adds the partials in the fixed order, solves, updates the pose and evaluates the stop rule.
-__device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, float* acc, int cnt) {
+// L: the state as it was when the launch began (the kernel's shared-memory copy, or S itself): the last CTA's serial
+// tail then reads no global memory but the partials.
+__device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, float* acc, int cnt, const BigState* L) {
   BigState* S = a.w.st;
   __shared__ float s_sum[8];
   __shared__ int s_cnt[8];
   __shared__ bool s_last;
-  cta_partials<6>(acc, a.w.part);
-  // visible points of this CTA (integers: order-independent)
+  // visible points of this CTA (integers: order-independent); published as slot 6 of the CTA's partials
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __threadfence();                         // this CTA's partial sums are visible before its ticket is
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  cta_partials<6>(acc, a.w.part);          // (has a CTA barrier before its stores)
+  if (threadIdx.x == 6) {
     int c = 0;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) c += s_cnt[wv];
-    if (c) atomicAdd(&S->nvis, c);
-    __threadfence();
-    s_last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
+    a.w.part[blockIdx.x * 21 + 6] = __int_as_float(c);
   }
+  __threadfence();                         // this CTA's partial sums are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&S->ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
   // ---- the last CTA: 9a fixed-order sum of the CTA partials, 9b solve, 10 update, stop rule -----------------------
@@ -549,12 +568,20 @@ __device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ncta = gridDim.x;
     // same order as finish_partials<6> (per thread: CTAs tid, tid + 256, ... ascending; warp tree; warps ascending);
     // all of a thread's partials are loaded (past L1) before the first addition: one L2 round trip, not eighteen
-    float v[3][6];
+    float v[3][7];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int c = threadIdx.x + j * 256;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) v[j][k] = c < ncta ? __ldcg(a.w.part + c * 21 + k) : 0.0f;
+      for (int k = 0; k < 7; ++k) v[j][k] = c < ncta ? __ldcg(a.w.part + c * 21 + k) : 0.0f;
+    }
+    {
+      int nv = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) nv += __float_as_int(v[j][6]);
+      for (int c = threadIdx.x + 768; c < ncta; c += blockDim.x) nv += __float_as_int(__ldcg(a.w.part + c * 21 + 6));
+      for (int o = 16; o > 0; o >>= 1) nv += __shfl_down_sync(0xffffffffu, nv, o);
+      if (lane == 0) s_cnt[warp] = nv;
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -578,26 +605,30 @@ __device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, floa
     const ict_optparam& op = a.prm.op;
     float sumsd[6], dp[6];
     for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
-    lu6_solve_exact(S->lu, sumsd, dp);   // == lu6_solve, straight-line
-    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
-    se3_exp<float>(S->G, S->p);
+    lu6_solve_exact(L->lu, sumsd, dp);   // == lu6_solve, straight-line
+    float pnew[6];
+    for (int k = 0; k < 6; ++k) { pnew[k] = L->p[k] + dp[k]; S->p[k] = pnew[k]; }
+    se3_exp<float>(S->G, pnew);
     const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
-    if (S->it == 0) S->normdp_init = normdp;
+    const int it = L->it;
+    const float normdp_init = it == 0 ? normdp : L->normdp_init;
+    if (it == 0) S->normdp_init = normdp;
     S->normdp = normdp;
-    const int nvis = *(volatile int*)&S->nvis;
-    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
-      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
+    int nvis = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) nvis += s_cnt[wv];
+    if (a.prm.trace && L->trace_n < a.prm.trace_cap) {
+      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + L->trace_n) * ICT_TRACE_FLOATS;
+      S->trace_n = L->trace_n + 1;
       rec[0] = (float)sl;
-      rec[1] = (float)S->it;
+      rec[1] = (float)it;
       for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
       rec[14] = normdp;
       rec[15] = (float)nvis;
       for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
     }
-    S->npix += (long long)nvis * op.novals;
-    S->nvis = 0;
-    S->it += 1;
-    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+    S->npix = L->npix + (long long)nvis * op.novals;
+    S->it = it + 1;
+    S->cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);
     S->ticket = 0;
   }
 }
@@ -662,7 +693,7 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter(const BigArgs a, int sl) 
       ++cnt;
     }
   }
-  dense_iter_finish(a, sl, acc, cnt);
+  dense_iter_finish(a, sl, acc, cnt, S);
 }
 
 // The same iteration with the five streams of a point (X, Y, Z, ref, sd1..6: 40 B) staged through shared memory by
@@ -671,37 +702,27 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter(const BigArgs a, int sl) 
 // four-texel gather (two tiles per trip, for more gathers in flight, was not faster: 35 vs 33 us).  CTA b takes the tiles b, b + G, b + 2G, ... and thread t the point t of each — the partition
 // and order of the grid-stride loop above, hence the same sums bit for bit.  Needs 16-byte aligned streams
 // (point count a multiple of 4); the launcher falls back to k_dense_iter otherwise.
-#define DENSE_NST 3
+template <int NST>
 __global__ void __launch_bounds__(256, 4) k_dense_iter_tma(const BigArgs a, int sl) {
   BigState* S = a.w.st;
-  if (!S->cont) return;
-  __shared__ __align__(128) float s_buf[DENSE_NST][10][256];
-  __shared__ unsigned long long s_full[DENSE_NST];
-  __shared__ float s_G[12];
+  extern __shared__ __align__(128) unsigned char dense_smem[];
+  float (*s_buf)[10][256] = reinterpret_cast<float (*)[10][256]>(dense_smem);
+  __shared__ unsigned long long s_full[NST];
+  __shared__ BigState s_S;                 // the state when this launch began: pose, LU factors, counters
   const int tid = threadIdx.x;
-  if (tid < 12) s_G[tid] = S->G[tid];
-  if (tid == 0) {
-    for (int k = 0; k < DENSE_NST; ++k) mbar_init(&s_full[k], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  float G[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) G[k] = s_G[k];
-  const CamLevels& cam = a.prm.cam;
-  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
-  const int width = cam.width[sl];
-  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  // ---- before the previous launch has finished (programmatic dependent launch): nothing here reads what an
+  // iteration writes; the streams of the first NST tiles are requested already -------------------------------------
   const int64_t off = a.prm.pt_off[a.t];
   const float* q = a.prm.pt3d + 3 * off;
   const long long P = a.P;
   const float* sdp = a.w.coef;
   const int ntile = (int)((P + 255) / 256);
-  const int nmine = ntile > (int)blockIdx.x ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  int nmine = ntile > (int)blockIdx.x ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (a.prm.dbg_skip_serial == 4) nmine = 0;                                   // DBG: launch + finish only
   auto issue = [&](int n) {               // thread 0: the n-th tile of this CTA into stage n % NST
     const long long i0 = ((long long)blockIdx.x + (long long)n * gridDim.x) * 256;
     const unsigned bytes = (unsigned)((P - i0 < 256 ? P - i0 : 256) * 4);
-    const int st = n % DENSE_NST;
+    const int st = n % NST;
     mbar_expect_tx(&s_full[st], 10 * bytes);
     bulk_g2s(s_buf[st][0], q + i0, bytes, &s_full[st]);
     bulk_g2s(s_buf[st][1], q + a.n_in + i0, bytes, &s_full[st]);
@@ -710,15 +731,37 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter_tma(const BigArgs a, int 
 #pragma unroll
     for (int k = 0; k < 6; ++k) bulk_g2s(s_buf[st][4 + k], sdp + k * P + i0, bytes, &s_full[st]);
   };
-  if (tid == 0)
-    for (int n = 0; n < DENSE_NST && n < nmine; ++n) issue(n);
+  if (tid == 0) {
+    for (int k = 0; k < NST; ++k) mbar_init(&s_full[k], 1);
+    mbar_fence_init();
+    for (int n = 0; n < NST && n < nmine; ++n) issue(n);
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next iteration may become resident as CTAs retire
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // the previous launch is complete and visible
+  if (tid < (int)(sizeof(BigState) / 4)) reinterpret_cast<int*>(&s_S)[tid] = reinterpret_cast<const int*>(S)[tid];
+  __syncthreads();
+  if (!s_S.cont) {                         // converged: the requested tiles must land before the CTA may retire
+    if (tid == 0)
+      for (int n = 0; n < NST && n < nmine; ++n) mbar_wait(&s_full[n], 0);
+    return;
+  }
+  float G[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) G[k] = s_S.G[k];
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl];
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
   float acc[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = 0.0f;
   int cnt = 0;
-  // one point of a staged tile: projection, placement, the four-texel gather (returns the sample, sets vis)
+  const int dbg = a.prm.dbg_skip_serial;
+  // one point of a staged tile: projection, placement, the four-texel gather (returns the sample, sets vis).
+  // (Tried: placing tile n+1 and issuing its gather before folding tile n — 23.1 instead of 21.3 us per iteration.)
   auto sample = [&](int st, bool& vis) -> float {
     const float X = s_buf[st][0][tid], Y = s_buf[st][1][tid], Z = s_buf[st][2][tid];
+    if (dbg == 2) { vis = true; return X + Y + Z; }                            // DBG: streams only
     const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];                    // project_pt, pose.cpp:307-397
     const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
     const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
@@ -730,9 +773,9 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter_tma(const BigArgs a, int 
     return bilin4(Inew, pp.base, width, pp.w0, pp.w1, pp.w2, pp.w3);
   };
   for (int n = 0; n < nmine; ++n) {
-    const int st = n % DENSE_NST;
+    const int st = n % NST;
     const long long i = ((long long)blockIdx.x + (long long)n * gridDim.x) * 256 + tid;
-    mbar_wait(&s_full[st], (n / DENSE_NST) & 1);
+    mbar_wait(&s_full[st], (n / NST) & 1);
     bool vis = false;
     float pn = 0.0f;
     if (i < P) pn = sample(st, vis);
@@ -743,9 +786,9 @@ __global__ void __launch_bounds__(256, 4) k_dense_iter_tma(const BigArgs a, int 
       ++cnt;
     }
     __syncthreads();                       // every thread has read the stage
-    if (tid == 0 && n + DENSE_NST < nmine) issue(n + DENSE_NST);
+    if (tid == 0 && n + NST < nmine) issue(n + NST);
   }
-  dense_iter_finish(a, sl, acc, cnt);
+  dense_iter_finish(a, sl, acc, cnt, &s_S);
 }
 
 __global__ void k_big_level_end(const BigArgs a, int sl) {
@@ -782,15 +825,35 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const bool ex = prm.sum_mode != 0;   // reference-order sums
   const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !getenv("ICT_DENSE_V1");
   int nl = 0;
-  k_big_init<<<ncta, 256, 0, st>>>(a); ++nl;
+  k_big_init<<<ncta, 256, 0, st>>>(a, fused ? 1 : 0); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
   for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
     k_dense_level<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
     // bulk-copy staging needs 16-byte aligned streams: point counts and the track's offset multiples of four
     const bool tma = t == 0 && (a.P % 4 == 0) && (a.n_in % 4 == 0) && !getenv("ICT_DENSE_LDG");   // t == 0: offset 0
+    static int nst = 0, pdl = 1;
+    if (!nst) {
+      nst = getenv("ICT_DENSE_NST") ? atoi(getenv("ICT_DENSE_NST")) : 3;     // A/B knobs
+      pdl = getenv("ICT_DENSE_NOPDL") ? 0 : 1;
+      cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 10240);
+      cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+    // programmatic dependent launch: iteration k+1 becomes resident while the last CTA of iteration k still runs the
+    // solve, and its first tiles are in flight by the time the pose is published
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = pdl;
+    cfg.gridDim = dim3(ncta);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cfg.attrs = lattr;
+    cfg.numAttrs = 1;
     for (int it = 0; it < op.maxiter; ++it) {
-      if (tma) k_dense_iter_tma<<<ncta, 256, 0, st>>>(a, sl); else k_dense_iter<<<ncta, 256, 0, st>>>(a, sl);
+      if (tma && nst == 3) { cfg.dynamicSmemBytes = 3 * 10240; cudaLaunchKernelEx(&cfg, k_dense_iter_tma<3>, a, sl); }
+      else if (tma) { cfg.dynamicSmemBytes = 5 * 10240; cudaLaunchKernelEx(&cfg, k_dense_iter_tma<5>, a, sl); }
+      else k_dense_iter<<<ncta, 256, 0, st>>>(a, sl);
       ++nl;
     }
     k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
