@@ -167,8 +167,33 @@ def other_configs(ict, dev):
                           % (n, iters), "ms_per_trackpose": 1e3 * best, "value": npix / best,
                           "unit": "pixel-residuals/s", "algorithmic_GBps": 44.0 * npix / best / 1e9,
                           "note": "host call incl. launches and result copy; 44 B per pixel-residual (SURVEY.md 8d); "
-                                  "per-iteration kernel: profiles/r01_dense_launches.csv"}
-    tr.close(); fr.close()
+                                  "per-iteration kernel: iteration_kernel below and profiles/r01_dense_launches.csv"}
+    tr.close()
+    # the streaming iteration kernel alone: slope between runs of 2 and 10 iterations per level (the stop rule off)
+    tt = {}
+    for mi in (2, 10):
+        op2 = ict.make_optparam(lv_f=3, lv_l=0, psz=1, maxiter=mi, normdp_ratio=1e-30, donorm=0, dopatchnorm=0, maxpttrack=n)
+        tr = ict.Tracker(op2, sc.fc, sc.cc, sc.wh)
+        tr.set_points(np.array([0, n], np.int64), pts.copy())
+        bt = None
+        for rep in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r2 = tr.track_batch(fr, 0, 1, np.zeros((1, 6)))
+            dt = time.perf_counter() - t0
+            bt = dt if bt is None or dt < bt else bt
+        tt[mi] = bt
+        tr.close()
+    per_it = (tt[10] - tt[2]) / 32.0
+    peak, peak_src = read_peaks()
+    out["dense_1080p"]["iteration_kernel"] = {
+        "name": "k_dense_iter_tma<3>", "us_per_launch": 1e6 * per_it, "bytes_per_point": 44,
+        "achieved_GBps": 44.0 * n / per_it / 1e9, "peak_GBps": peak, "frac": 44.0 * n / per_it / 1e9 / peak,
+        "fixed_us_per_trackpose": 1e6 * (tt[2] - 8 * per_it),
+        "method": "(t[10 iterations/level] - t[2 iterations/level]) / 32 launches, stop rule off; includes launch and "
+                  "the last CTA's solve; 44 B per point = 40 B streamed (X, Y, Z, ref, sd1..6) + one 4 B texel "
+                  "(SURVEY.md 8d)"}
+    fr.close()
     # ---- configs[1]: run_track_nposes-style chain, 100 frames, 640x480, psz 8, 100 points; 256 pose samples ----
     NF, S = 100, 256
     sc, frames, poses = synth.make_sequence(5, NF, 640, 480)
@@ -457,7 +482,7 @@ def main():
                                      "is resident in shared memory, so measured DRAM traffic (`traffic`, ncu) is ~0.1 % "
                                      "of it and frac > 1; the kernel is issue/latency-bound (issue slots 58 % busy, "
                                      "profiles/r01_k_track_v2_ncu_summary.txt). The HBM-streaming kernel of the path is "
-                                     "the dense iteration (other_configs.dense_1080p: 49 % of the measured bandwidth)"},
+                                     "the dense iteration (other_configs.dense_1080p.iteration_kernel, measured in this run)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if e2e:
             line["e2e"] = {"value": npix_job * a.steps / (ms_e2e_all * 1e-3), "unit": "pixel-residuals/s",

@@ -20,5 +20,5 @@ for mi in (2, 10):
     res[mi] = best
     print("maxiter %d: iters %s  %.3f ms" % (mi, out["iters"][0].tolist(), 1e3 * best))
 per = (res[10] - res[2]) / 32
-print("per iteration launch %.2f us (%.0f GB/s of 40 B per point), fixed %.0f us per TrackPose" % (
-    1e6 * per, c["npts"] * 40 / per / 1e9, 1e6 * (res[2] - 8 * per)))
+print("per iteration launch %.2f us (%.0f GB/s at 44 B per point: 40 B streamed + 4 B texel), fixed %.0f us per TrackPose" % (
+    1e6 * per, c["npts"] * 44 / per / 1e9, 1e6 * (res[2] - 8 * per)))

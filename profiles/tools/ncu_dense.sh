@@ -1,4 +1,4 @@
-# one --set full capture of the dense level-0 iteration kernel (the largest launches: skip the coarse levels)
+# one --set full capture of a dense iteration launch (every level works on all 1 978 624 points)
 set -e
 timeout 300 python profiles/tools/run_dense.py > gpurun_out/dense_plain.log 2>&1
 tail -1 gpurun_out/dense_plain.log
