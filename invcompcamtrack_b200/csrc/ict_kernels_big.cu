@@ -273,8 +273,12 @@ __global__ void __launch_bounds__(256) k_big_level_hessian(const BigArgs a) {
   cta_partials<21>(acc, a.w.part);
 }
 
+// (griddepcontrol.*: no-ops unless the launch carries the programmatic-dependent-launch attribute, as the fused dense
+// path's launches do — the kernel then becomes resident while its predecessor drains, and lets its successor do so)
 __global__ void __launch_bounds__(256) k_big_level_finish(const BigArgs a, int sl) {
   __shared__ float s_H[21];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   finish_partials<21>(a.w.part, a.w.ncta, s_H);
   if (threadIdx.x < 32) lu6_factor_warp(s_H, a.w.st->lu);
   if (threadIdx.x == 0) {
@@ -285,8 +289,8 @@ __global__ void __launch_bounds__(256) k_big_level_finish(const BigArgs a, int s
     S->it = 0;
     S->nvis = 0;
     S->cont = (0 < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+    if (a.prm.iters) a.prm.iters[(int64_t)a.t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = 0;
   }
-  (void)sl;
 }
 
 __global__ void k_big_iter_points(const BigArgs a, int sl) {
@@ -506,6 +510,8 @@ __global__ void __launch_bounds__(256, 4) k_dense_level(const BigArgs a, int sl)
   const float* __restrict__ Dyr = a.prm.frames[rf].dy[sl];
   const long long P = a.P;
   float* sdp = a.w.coef;                   // sd_k of point i at sdp[k * P + i] (the coefficient region, 10 P floats)
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // the previous level's iterations are complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   float acc[21];
 #pragma unroll
   for (int k = 0; k < 21; ++k) acc[k] = 0.0f;
@@ -628,6 +634,7 @@ __device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, floa
     }
     S->npix = L->npix + (long long)nvis * op.novals;
     S->it = it + 1;
+    if (a.prm.iters) a.prm.iters[(int64_t)a.t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = it + 1;
     S->cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);
     S->ticket = 0;
   }
@@ -828,8 +835,6 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   k_big_init<<<ncta, 256, 0, st>>>(a, fused ? 1 : 0); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
   for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
-    k_dense_level<<<ncta, 256, 0, st>>>(a, sl); ++nl;
-    k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
     // bulk-copy staging needs 16-byte aligned streams: point counts and the track's offset multiples of four
     const bool tma = t == 0 && (a.P % 4 == 0) && (a.n_in % 4 == 0) && !getenv("ICT_DENSE_LDG");   // t == 0: offset 0
     static int nst = 0, pdl = 1;
@@ -850,13 +855,17 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
     cfg.stream = st;
     cfg.attrs = lattr;
     cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_dense_level, a, sl); ++nl;
+    cfg.gridDim = dim3(1);
+    cudaLaunchKernelEx(&cfg, k_big_level_finish, a, sl); ++nl;
+    cfg.gridDim = dim3(ncta);
     for (int it = 0; it < op.maxiter; ++it) {
       if (tma && nst == 3) { cfg.dynamicSmemBytes = 3 * 10240; cudaLaunchKernelEx(&cfg, k_dense_iter_tma<3>, a, sl); }
       else if (tma) { cfg.dynamicSmemBytes = 5 * 10240; cudaLaunchKernelEx(&cfg, k_dense_iter_tma<5>, a, sl); }
       else k_dense_iter<<<ncta, 256, 0, st>>>(a, sl);
       ++nl;
     }
-    k_big_level_end<<<1, 1, 0, st>>>(a, sl); ++nl;
+    // (no k_big_level_end: the iteration's serial tail records the level's iteration count)
   }
   for (int sl = op.lv_f; sl >= op.lv_l && !fused; --sl) {
     k_big_level_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
