@@ -381,6 +381,7 @@ struct ict_tracker {
   bool have_2d = false;
   int sum_mode = 0;
   int force_general = 0;
+  int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, ticket;
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
@@ -536,6 +537,8 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.t0 = 0;
   prm.sum_mode = tr->sum_mode;
   prm.force_general = tr->force_general;
+  prm.seq_n = tr->seq_n;
+  prm.seq_step = tr->seq_step;
   prm.dbg_skip_serial = getenv("ICT_DBG_SKIP_SERIAL") ? atoi(getenv("ICT_DBG_SKIP_SERIAL")) : 0;
   prm.serial_warp_last = getenv("ICT_SERIAL_WARP_LAST") ? 1 : 0;
   prm.v2_lu_setup = getenv("ICT_V2_LU") ? 1 : 0;
@@ -663,12 +666,22 @@ int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nst
   CU(tr->npix.reserve(sizeof(long long) * (size_t)T * (nsteps ? nsteps : 1)));
   double* chain = tr->p_out.as<double>();
   CU(cudaMemcpyAsync(chain, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
-  for (int k = 0; k < nsteps; ++k) {
-    const int fr = first + k * step;
-    int rc = run_tracks(tr, fs, nullptr, nullptr, fr, fr + step, chain + (size_t)k * 6 * T,
-                        chain + (size_t)(k + 1) * 6 * T, tr->iters.as<int>() + (size_t)k * T * L, nullptr, 0,
-                        tr->npix.as<long long>() + (size_t)k * T, 0);
+  if (nsteps > 1 && track_chain_in_one_launch(tr->op, tr->max_pts, tr->sum_mode, tr->force_general)) {
+    // K2v8 loops over the frames inside the kernel: one launch for the whole chain
+    tr->seq_n = nsteps;
+    tr->seq_step = step;
+    int rc = run_tracks(tr, fs, nullptr, nullptr, first, first + step, chain, chain + (size_t)6 * T, tr->iters.as<int>(),
+                        nullptr, 0, tr->npix.as<long long>(), 0);
+    tr->seq_n = tr->seq_step = 0;
     if (rc) return rc;
+  } else {
+    for (int k = 0; k < nsteps; ++k) {
+      const int fr = first + k * step;
+      int rc = run_tracks(tr, fs, nullptr, nullptr, fr, fr + step, chain + (size_t)k * 6 * T,
+                          chain + (size_t)(k + 1) * 6 * T, tr->iters.as<int>() + (size_t)k * T * L, nullptr, 0,
+                          tr->npix.as<long long>() + (size_t)k * T, 0);
+      if (rc) return rc;
+    }
   }
   CU(cudaMemcpyAsync(poses_out, chain, sizeof(double) * 6 * (size_t)T * (nsteps + 1), cudaMemcpyDeviceToHost, 0));
   if (iters && nsteps)

@@ -109,10 +109,20 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
   float* s_Yc = s_Xc + P;
   float* s_Zc = s_Yc + P;
 
-  const int rf = prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref;
-  const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
+  // A chain of frame steps (ict_track_sequence) runs in ONE launch: a track's step k+1 depends on its own step k only,
+  // so the CTA loops over the frames and no step waits for the slowest track of the previous one.  Every step starts
+  // from the top (reset, points, SetPose) exactly like a launch of its own: same results bit for bit.
+  const int nseq = prm.seq_n > 1 ? prm.seq_n : 1;
+  const int nlev = op.lv_f - op.lv_l + 1;
+  for (int sq = 0; sq < nseq; ++sq) {
+  const int rf = (prm.ref_frame ? prm.ref_frame[t] : prm.fixed_ref) + sq * prm.seq_step;
+  const int nf = (prm.new_frame ? prm.new_frame[t] : prm.fixed_new) + sq * prm.seq_step;
   const FrameDesc* fr_ref = prm.frames + rf;
   const FrameDesc* fr_new = prm.frames + nf;
+  const double* step_p_in = prm.p_in + (int64_t)sq * 6 * prm.T;
+  double* step_p_out = prm.p_out + (int64_t)sq * 6 * prm.T;
+  int* step_iters = prm.iters ? prm.iters + (int64_t)sq * prm.T * nlev : nullptr;
+  long long* step_npix = prm.npixres ? prm.npixres + (int64_t)sq * prm.T : nullptr;
   const int swarp = 0;
 
   // ---- ResetOdometer (odometer.cpp:580-609) + points -----------------------------------------------------------------
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
       for (int k = 0; k < 12; ++k) s_AB[i * 12 + k] = 0.0f;
     }
   }
-  if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
+  if (tid == 0) setpose_se3(step_p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
   __syncthreads();
   for (int i = tid; i < P; i += nt) {   // project_pt_save_rotated, pose.cpp:400-488
     const float X = s_X[i], Y = s_Y[i], Z = s_Z[i];
@@ -362,13 +372,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
       __syncthreads();
       ++it;
     }
-    if (tid == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
+    if (tid == 0 && step_iters) step_iters[(int64_t)t * nlev + (op.lv_f - sl)] = S.it;
   }
 
   if (warp == swarp && lane == 0) {
     getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
-                prm.p_out + 6 * (int64_t)t);
-    if (prm.npixres) prm.npixres[t] = (long long)nvsum * N;
+                step_p_out + 6 * (int64_t)t);
+    if (step_npix) step_npix[t] = (long long)nvsum * N;
     if (trace)
       for (int k = trace_n; k < prm.trace_cap; ++k) {
         float* rec = trace + (int64_t)ICT_TRACE_FLOATS * k;
@@ -376,6 +386,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         rec[0] = -1.0f;
       }
   }
+  __syncthreads();                         // the step's pose is written (by thread 0, which reads it next) and shared
+  }                                        // memory is free for the next step
 }
 
 size_t v8_smem_bytes(const ict_optparam& op, int max_pts) {

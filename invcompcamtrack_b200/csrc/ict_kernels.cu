@@ -1242,8 +1242,17 @@ bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int f
   return !getenv("ICT_FAST_V1") && v8_supported(op, max_pts);
 }
 
+// True when launch_track runs K2v8 for this configuration: the kernel that can take a whole chain of frame steps
+// (TrackParams.seq_n) in one launch.
+bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general) {
+  return sum_mode == 0 && !force_general && !getenv("ICT_FAST_V1") && !getenv("ICT_PIPE") && !getenv("ICT_SEQ_LAUNCHES") &&
+         v8_supported(op, max_pts);
+}
+
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
+  if (prm.seq_n > 1 && !track_chain_in_one_launch(prm.op, max_pts, prm.sum_mode, prm.force_general))
+    return cudaErrorInvalidConfiguration;   // only K2v8 loops over frames
   const size_t smem = track_smem_bytes(prm.op, max_pts, prm.sum_mode);
   if (!track_fits_one_cta(prm.op, max_pts, prm.sum_mode, prm.force_general)) return cudaErrorInvalidConfiguration;
   const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;

@@ -43,6 +43,9 @@ struct TrackParams {
   int dbg_skip_serial;             // profiling experiment: skip solve/update (results meaningless)
   int v2_lu_setup;                 // K2v2 A/B knob: per-level solve matrix from the warp LU instead of the sweeps
   int force_general;               // 1: always use the general kernel k_track (tests compare the two)
+  int seq_n, seq_step;             // K2v8 only: seq_n > 1 runs a whole chain in one launch — step k tracks frame
+                                   //    fixed_ref + k*seq_step -> + seq_step from pose p_in + 6*T*k to p_out + 6*T*k
+                                   //    (iters + T*L*k, npixres + T*k); 0/1: a single step
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
                                    //    with the oracle's default model of the reference, ~3x slower)
 };
@@ -63,6 +66,7 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 // Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int force_general);
+bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
 // K2v2 (ict_kernel_v2.cu): the production kernel for psz 32 without dopatchnorm, tree sums; launch_track routes

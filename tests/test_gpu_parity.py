@@ -182,6 +182,39 @@ def test_sequence_chain(ict, orc):
     assert np.abs(b["poses"][-1, 0]).max() < 2e-2
 
 
+@pytest.mark.parametrize("kw", [dict(npts=60, S=7), dict(npts=150, S=3, donorm=1, dopatchnorm=1)])
+def test_chain_in_one_launch_equals_per_frame_launches(ict, kw):
+    """ict_track_sequence with psz 8 in the default order: K2v8 loops over the frames inside ONE launch (a track's step
+    k+1 depends on its own step k only).  Same poses, iteration counts and pixel-residual counts, bit for bit, as one
+    launch per frame (ICT_SEQ_LAUNCHES=1), forwards and backwards."""
+    import os
+    from invcompcamtrack_b200 import synth
+    nfr, S, n = 6, kw["S"], kw["npts"]
+    sc, frames, poses = synth.make_sequence(3, nfr, 320, 240)
+    op = ict.make_optparam(lv_f=2, psz=8, maxpttrack=n, donorm=kw.get("donorm", 0), dopatchnorm=kw.get("dopatchnorm", 0))
+    fr = ict.Frames(nfr, 320, 240, 2, 8)
+    fr.upload(0, np.stack(frames))
+    tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_points(np.arange(S + 1, dtype=np.int64) * n, np.concatenate([sc.points(70 + s, n, 8, 2) for s in range(S)]))
+    p0 = np.zeros((S, 6))
+    p0[:, 3] = np.linspace(-0.01, 0.01, S)          # chains that start apart
+    try:
+        os.environ.pop("ICT_SEQ_LAUNCHES", None)
+        a = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
+        ab = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, a["poses"][-1])
+        os.environ["ICT_SEQ_LAUNCHES"] = "1"
+        b = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
+        bb = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, b["poses"][-1])
+    finally:
+        os.environ.pop("ICT_SEQ_LAUNCHES", None)
+    for x, y in ((a, b), (ab, bb)):
+        assert np.array_equal(x["poses"], y["poses"])
+        assert np.array_equal(x["iters"], y["iters"]) and np.array_equal(x["npixres"], y["npixres"])
+    if not kw.get("donorm"):                                          # and the chains follow the motion
+        assert np.abs(a["poses"][-1] - poses[-1]).max() < 5e-2
+    tr.close(); fr.close()
+
+
 @pytest.mark.parametrize("kw", [dict(seed=61, w=320, h=240, lv_f=2, psz=1, dense_border=8, tilt=(0.15, -0.1)),
                                 dict(seed=62, w=320, h=240, lv_f=2, psz=1, dense_border=6, tilt=(0.1, 0.2), donorm=1),
                                 dict(seed=63, w=160, h=120, lv_f=1, psz=8, npts=900),
