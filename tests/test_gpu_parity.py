@@ -377,14 +377,15 @@ def test_psz8_kernel_edge_cases(ict, orc, kw):
     assert np.abs(gg["trace"][:, 0, 2:8] - g["trace"][:, 0, 2:8]).max() <= 1e-5 * np.abs(o["trace"][:, 0, 16:22]).max()
 
 
-def test_psz8_kernel_points_out_of_view(ict, orc):
-    case = make_case(psz=8, seed=79, npts=40, ntracks=10)
+@pytest.mark.parametrize("npts", [40, 150])      # K2v8 with eight and with sixteen warps
+def test_psz8_kernel_points_out_of_view(ict, orc, npts):
+    case = make_case(psz=8, seed=79, npts=npts, ntracks=10)
     T = case["T"]
     p_in = np.zeros((T, 6))
     p_in[:, 0] = np.linspace(0.5, 2.2, T)
     p_in[:, 4] = 0.02
     o = oracle_run(orc, case, trace_cap=48, p_in=p_in)
-    assert (o["trace"][:, 0, 15] < 40).any() and (o["trace"][:, 0, 15] > 0).any()
+    assert (o["trace"][:, 0, 15] < npts).any() and (o["trace"][:, 0, 15] > 0).any()
     assert_bit_identical(gpu_run(ict, case, trace_cap=48, sum_order=1, p_in=p_in), o)
     g = gpu_run(ict, case, trace_cap=48, p_in=p_in)
     res = check_parity(g, o, case, gates=False)
