@@ -152,7 +152,9 @@ int ict_track_batch_dev(ict_tracker* tr, const ict_frames* fs, const int* ref_fr
 
 /* One forward (step=+1) or backward (step=-1) chain of run_track_nposes.cpp:232-239 / :251-258 for all T tracks:
  * for k in 0..nsteps-1: SetPose(p, frame[first+k*step] as ref, frame[first+(k+1)*step] as new); TrackPose(p).
- * poses_out: double[(nsteps+1)*T*6], entry 0 = p_in. Host buffers. */
+ * poses_out: double[(nsteps+1)*T*6], entry 0 = p_in. Host buffers.  The poses of the chain never leave the device
+ * between steps; with 8x8 patches in the default summation order the whole chain is one kernel launch (a track's step
+ * depends on its own previous step only), otherwise one launch per step: same results either way. */
 int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nsteps, int step,
                        const double* p_in, double* poses_out, int* iters, int64_t* npixres);
 
