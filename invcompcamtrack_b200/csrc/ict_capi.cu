@@ -382,6 +382,7 @@ struct ict_tracker {
   int sum_mode = 0;
   int force_general = 0;
   int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
+  const int *big_rf = nullptr, *big_nf = nullptr;   // set by ict_track_batch around run_tracks: per-track frames (host) of the multi-CTA path
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, ticket;
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
@@ -557,10 +558,15 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
     if (tr->h_off.empty()) return fail(ICT_ERR_UNSUPPORTED, "big tracks need host-side pt_off (use ict_tracker_set_points)");
     if (rf_dev) return fail(ICT_ERR_UNSUPPORTED, "big tracks take fixed ref/new frames (use ict_track_sequence or T=1)");
+    size_t wb = 0;                          // one work buffer, sized for the largest track, reused in stream order
+    for (int t = 0; t < tr->T; ++t) {
+      const size_t w = bigtrack_work_bytes(tr->op, tr->h_off[t + 1] - tr->h_off[t]);
+      wb = w > wb ? w : wb;
+    }
+    CU(tr->big.reserve(wb));
     for (int t = 0; t < tr->T; ++t) {
       const int64_t n = tr->h_off[t + 1] - tr->h_off[t];
-      const size_t wb = bigtrack_work_bytes(tr->op, n);
-      CU(tr->big.reserve(wb));
+      if (tr->big_rf) { prm.fixed_ref = tr->big_rf[t]; prm.fixed_new = tr->big_nf[t]; }
       CU(launch_track_big(prm, t, n, tr->big.p, st));
     }
   }
@@ -598,11 +604,13 @@ int ict_track_batch(ict_tracker* tr, const ict_frames* fs, const int* ref_frame,
   const bool big = !track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general);
   int rc;
   if (big) {
-    // multi-CTA path runs one track at a time with fixed frames
-    if (T != 1) return fail(ICT_ERR_UNSUPPORTED, "tracks too large for one CTA: pass them one per call (T=1)");
+    // multi-CTA path: the tracks run one after the other on the stream, each with its own frame pair
+    tr->big_rf = ref_frame;
+    tr->big_nf = new_frame;
     rc = run_tracks(tr, fs, nullptr, nullptr, ref_frame[0], new_frame[0], tr->p_in.as<double>(), tr->p_out.as<double>(),
                     tr->iters.as<int>(), trace && trace_cap > 0 ? tr->trace.as<float>() : nullptr, trace_cap,
                     tr->npix.as<long long>(), 0);
+    tr->big_rf = tr->big_nf = nullptr;
   } else {
     rc = run_tracks(tr, fs, tr->rf.as<int>(), tr->nf.as<int>(), -1, -1, tr->p_in.as<double>(), tr->p_out.as<double>(),
                     tr->iters.as<int>(), trace && trace_cap > 0 ? tr->trace.as<float>() : nullptr, trace_cap,

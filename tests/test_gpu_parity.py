@@ -244,6 +244,20 @@ def test_dense_alignment_multi_cta_path(ict, orc, kw):
     print(res, g["iters"], o["iters"])
 
 
+def test_several_large_tracks_per_call(ict, orc):
+    """Tracks beyond one CTA (300 points of 8x8 pixels) in one ict_track_batch call: the multi-CTA path takes them one
+    after the other on the stream.  Reference order: bit-identical to the oracle, track by track."""
+    case = make_case(psz=8, seed=85, npts=300, ntracks=3, w=640, h=480)
+    o = oracle_run(orc, case, trace_cap=48)
+    gx = gpu_run(ict, case, trace_cap=48, sum_order=1)
+    assert np.array_equal(gx["pt2d"], o["pt2d"])
+    assert_bit_identical(gx, o)
+    g = gpu_run(ict, case, trace_cap=48)
+    res = check_parity(g, o, case, gates=False)
+    assert res["jtr_first"] <= 1e-5, res
+    assert np.abs(g["p_out"] - o["p_out"]).max() < 1e-3, res
+
+
 def test_ncc_scoring(ict, orc):
     """run_track_nposes.cpp:271-355 on the GPU vs the oracle: per-point weighted NCC of back / reference / forward
     patches, including points outside the frames (corr = -1 when the reference point is out, weight 0 otherwise)."""
