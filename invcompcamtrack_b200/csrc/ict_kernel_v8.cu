@@ -1,9 +1,10 @@
 // ict_kernel_v8.cu — K2v8: SetPose + TrackPose for 8x8 patches (the reference's own configuration: psz 8, ~100
 // points per track, optionally dopatchnorm — run_io_reprojection_test.cpp:15, run_odometer_test.m:232), default
-// (tree) summation order, up to 128 points per track.  The scheme of K2v2 (ict_kernel_v2.cu) with the roles
+// (tree) summation order, up to 240 points per track (8 warps up to 128 points, 16 beyond; shared memory bounds
+// it), optionally a whole chain of frame steps per launch.  The scheme of K2v2 (ict_kernel_v2.cu) with the roles
 // re-cut for many small patches:
 //
-//  * a warp owns the points w, w+8, w+16, ... of the track (w = warp) and processes one 8x8 patch per step: lane l
+//  * a warp owns the points w, w+NW, w+2NW, ... of the track (w = warp, NW = 8 or 16 warps) and processes one 8x8 patch per step: lane l
 //    takes the pixels (2j, c) and (2j+1, c), j = l/8, c = l%8, so the three rows it needs are loaded once (six
 //    read-only loads per plane) and the template of its two pixels is one float2 per plane (3 x LDS.64);
 //  * the placement (project_pt + util_getPatch's ceil/floor/weights, unfused, bit-exact pixel indexing) of all the

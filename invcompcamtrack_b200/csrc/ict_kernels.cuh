@@ -74,8 +74,8 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
 size_t v2_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
-// K2v8 (ict_kernel_v8.cu): the K2v2 scheme for 8x8 patches (the reference's own configuration), up to 128 points per
-// track, with or without dopatchnorm, tree sums.
+// K2v8 (ict_kernel_v8.cu): the K2v2 scheme for 8x8 patches (the reference's own configuration), up to 240 points per
+// track, with or without dopatchnorm, tree sums; honours TrackParams.seq_n (a chain of frame steps in one launch).
 bool v8_supported(const ict_optparam& op, int max_pts);
 size_t v8_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_v8(const TrackParams& prm, int max_pts, cudaStream_t stream);
