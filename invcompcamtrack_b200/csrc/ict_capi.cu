@@ -2,6 +2,7 @@
 // Every compute entry point runs CUDA kernels from ict_kernels.cu; there is no CPU fallback.
 #include "ict_kernels.cuh"
 
+#include <cuda.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -196,10 +197,81 @@ struct ict_frames {
   int sw[ICT_MAX_LEVELS], sh[ICT_MAX_LEVELS];
   float *I, *dx, *dy;
   FrameDesc* desc;
+  void* tmaps;        // device: CUtensorMap [nframes][3 planes][ICT_MAX_LEVELS], or null (geometry not TMA-able)
+  bool tma_ok;        // every entry of desc carries tensor maps (a view: every frame aliased so far does)
   DevBuf stage;
   CopyLane lane;
   bool view;
 };
+
+// ---- tensor maps of the padded level planes (K2r stages its windows with cp.async.bulk.tensor.2d) --------------------
+// One 2-D tiled map per frame, plane (I, dx, dy) and level: dimensions (sw, sh) floats, row pitch sw * 4 bytes, box
+// 40 x 17 floats = one half-patch window of a 32x32 patch (row above + 16 rows; column to the left + 32, starting at a
+// multiple of four columns because the innermost TMA coordinate has to be 16-byte aligned), no swizzle, no interleave.  TMA wants a 16-byte aligned base and a row pitch that
+// is a multiple of 16 bytes: with pad == 32 that holds whenever (w >> l) is a multiple of 4 on every level.
+// cuTensorMapEncodeTiled is reached through the runtime's driver entry point query: libictrack.so does not link
+// libcuda.
+typedef CUresult (*ict_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ict_encode_tiled_fn encode_tiled_fn() {
+  static ict_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (ict_encode_tiled_fn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+#define ICT_TMA_BOX_W 40
+#define ICT_TMA_BOX_H 17
+
+static bool frames_make_tmaps(ict_frames* fs) {
+  fs->tmaps = nullptr;
+  fs->tma_ok = false;
+  if (fs->pad != 32) return false;               // the box is the half-patch window of a 32x32 patch
+  ict_encode_tiled_fn enc = encode_tiled_fn();
+  if (!enc) return false;
+  for (int l = 0; l <= fs->lv_f; ++l)
+    if ((fs->sw[l] % 4) || (fs->level_off[l] % 4) || fs->sw[l] < ICT_TMA_BOX_W || fs->sh[l] < ICT_TMA_BOX_H) return false;
+  if (fs->plane_floats % 4) return false;
+  const size_t per_frame = 3 * ICT_MAX_LEVELS;
+  std::vector<CUtensorMap> maps(per_frame * fs->nframes);
+  memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+  float* planes[3] = {fs->I, fs->dx, fs->dy};
+  for (int f = 0; f < fs->nframes; ++f)
+    for (int q = 0; q < 3; ++q)
+      for (int l = 0; l <= fs->lv_f; ++l) {
+        void* base = planes[q] + (size_t)f * fs->plane_floats + fs->level_off[l];
+        const cuuint64_t dims[2] = {(cuuint64_t)fs->sw[l], (cuuint64_t)fs->sh[l]};
+        const cuuint64_t strides[1] = {(cuuint64_t)fs->sw[l] * sizeof(float)};
+        const cuuint32_t box[2] = {ICT_TMA_BOX_W, ICT_TMA_BOX_H};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&maps[(f * 3 + q) * ICT_MAX_LEVELS + l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return false;
+      }
+  if (cudaMalloc(&fs->tmaps, sizeof(CUtensorMap) * maps.size()) != cudaSuccess) {
+    cudaGetLastError();
+    fs->tmaps = nullptr;
+    return false;
+  }
+  if (cudaMemcpy(fs->tmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(fs->tmaps);
+    fs->tmaps = nullptr;
+    return false;
+  }
+  fs->tma_ok = true;
+  return true;
+}
 
 ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
   if (require_device()) return nullptr;
@@ -207,6 +279,8 @@ ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
   fs->nframes = nframes; fs->w = w; fs->h = h; fs->lv_f = lv_f; fs->pad = pad;
   fs->I = fs->dx = fs->dy = nullptr;
   fs->desc = nullptr;
+  fs->tmaps = nullptr;
+  fs->tma_ok = false;
   fs->view = false;
   fs->plane_floats = ict_pyramid_layout(w, h, lv_f, pad, fs->level_off, fs->sw, fs->sh);
   if (fs->plane_floats < 0 || nframes <= 0) {
@@ -222,9 +296,11 @@ ict_frames* ict_frames_create(int nframes, int w, int h, int lv_f, int pad) {
     ict_frames_destroy(fs);
     return nullptr;
   }
+  frames_make_tmaps(fs);       // optional: without them the reference-order path of psz 32 runs K2x instead of K2r
   std::vector<FrameDesc> d(nframes);
   for (int f = 0; f < nframes; ++f) {
     memset(&d[f], 0, sizeof(FrameDesc));
+    d[f].tmap = fs->tmaps ? (const char*)fs->tmaps + sizeof(CUtensorMap) * 3 * ICT_MAX_LEVELS * (size_t)f : nullptr;
     for (int l = 0; l <= lv_f; ++l) {
       d[f].I[l] = fs->I + (size_t)f * fs->plane_floats + fs->level_off[l];
       d[f].dx[l] = fs->dx + (size_t)f * fs->plane_floats + fs->level_off[l];
@@ -245,6 +321,7 @@ void ict_frames_destroy(ict_frames* fs) {
   if (fs->dx) cudaFree(fs->dx);
   if (fs->dy) cudaFree(fs->dy);
   if (fs->desc) cudaFree(fs->desc);
+  if (fs->tmaps) cudaFree(fs->tmaps);
   fs->stage.release();
   fs->lane.release();
   delete fs;
@@ -256,6 +333,8 @@ ict_frames* ict_frames_create_view(int nframes, int w, int h, int lv_f, int pad)
   fs->nframes = nframes; fs->w = w; fs->h = h; fs->lv_f = lv_f; fs->pad = pad;
   fs->I = fs->dx = fs->dy = nullptr;
   fs->desc = nullptr;
+  fs->tmaps = nullptr;
+  fs->tma_ok = true;           // until a frame without tensor maps is aliased
   fs->view = true;
   fs->plane_floats = ict_pyramid_layout(w, h, lv_f, pad, fs->level_off, fs->sw, fs->sh);
   if (fs->plane_floats < 0 || nframes <= 0 || cudaMalloc(&fs->desc, sizeof(FrameDesc) * nframes) != cudaSuccess) {
@@ -275,6 +354,7 @@ int ict_frames_alias(ict_frames* view, int idx, const ict_frames* src, int src_i
   if (view->w != src->w || view->h != src->h || view->lv_f != src->lv_f || view->pad != src->pad)
     return fail(ICT_ERR_BAD_ARG, "ict_frames_alias: geometry mismatch");
   CU(cudaMemcpyAsync(view->desc + idx, src->desc + src_idx, sizeof(FrameDesc), cudaMemcpyDeviceToDevice, 0));
+  view->tma_ok = view->tma_ok && src->tma_ok;
   return ICT_OK;
 }
 
@@ -537,6 +617,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.T = tr->T;
   prm.t0 = 0;
   prm.sum_mode = tr->sum_mode;
+  prm.tma_ok = fs->tma_ok ? 1 : 0;
   prm.force_general = tr->force_general;
   prm.seq_n = tr->seq_n;
   prm.seq_step = tr->seq_step;

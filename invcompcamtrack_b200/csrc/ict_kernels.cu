@@ -1275,6 +1275,9 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
   }
   if ((mode & 2) && !prm.force_general && !getenv("ICT_EXACT_V1") && kx8_supported(prm.op, max_pts))
     return launch_track_x8(prm, max_pts, stream);      // K2x8: reference-order sums, 8x8 patches, +/- dopatchnorm
+  if (mode == 2 && !prm.force_general && !getenv("ICT_EXACT_V1") && !getenv("ICT_EXACT_X") &&
+      kr_supported(prm.op, max_pts, prm.tma_ok))
+    return launch_track_r(prm, max_pts, stream);       // K2r: reference-order sums, resident sd images, TMA windows
   if (mode == 2 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_EXACT_V1") &&
       kx_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
     return launch_track_x(prm, max_pts, stream);       // K2x: reference-order sums, producer/chain warps

@@ -18,6 +18,9 @@ struct FrameDesc {
   const float* I[ICT_MAX_LEVELS];
   const float* dx[ICT_MAX_LEVELS];
   const float* dy[ICT_MAX_LEVELS];
+  const void* tmap;                // device array of CUtensorMap [3 planes: I, dx, dy][ICT_MAX_LEVELS] (128 bytes each):
+                                   //    2-D tiled maps of the padded level planes, box 40 x 17 floats (K2r); null when
+                                   //    the geometry does not allow TMA (row pitch not a multiple of 16 bytes)
 };
 
 struct TrackParams {
@@ -46,6 +49,8 @@ struct TrackParams {
   int seq_n, seq_step;             // K2v8 only: seq_n > 1 runs a whole chain in one launch — step k tracks frame
                                    //    fixed_ref + k*seq_step -> + seq_step from pose p_in + 6*T*k to p_out + 6*T*k
                                    //    (iters + T*L*k, npixres + T*k); 0/1: a single step
+  int tma_ok;                      // every frame of the store carries tensor maps (FrameDesc.tmap)
+  int r_pcap;                      // K2r: points per track the shared-memory layout is sized for (set by its launcher)
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
                                    //    with the oracle's default model of the reference, ~3x slower)
 };
@@ -85,6 +90,12 @@ cudaError_t launch_track_v8(const TrackParams& prm, int max_pts, cudaStream_t st
 // ICT_EXACT_V1 is set.
 size_t kx_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_x(const TrackParams& prm, int max_pts, cudaStream_t stream);
+
+// K2r (ict_kernel_r.cu): reference-order sums for psz 32 without dopatchnorm, up to 8 points per track, with the
+// steepest-descent images resident in shared memory and the windows staged by 2-D TMA; needs prm.tma_ok.
+bool kr_supported(const ict_optparam& op, int max_pts, int tma_ok);
+size_t kr_smem_bytes(const ict_optparam& op, int max_pts);
+cudaError_t launch_track_r(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
 // K2x8 (ict_kernel_x8.cu): reference-order sums for 8x8 patches (up to 224 points per track), with or without
 // dopatchnorm — bit-identical to the oracle like k_track<8,2|3>.
