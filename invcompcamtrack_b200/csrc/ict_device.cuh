@@ -88,6 +88,61 @@ __device__ __forceinline__ void se3_exp(T* G, const T* p) {
   G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
 }
 
+
+// The float instantiation of se3_exp with one change that cannot alter a bit: sig = sqrtf(x) instead of
+// (float)sqrt((double)x).  sqrt is correctly rounded in both precisions and 53 >= 2*24 + 2, so rounding the double
+// result to float equals the correctly rounded float root (no double-rounding case exists for square roots); the
+// double-precision root costs ~100 dependent cycles on the thread every other warp of the CTA waits for.  Everything
+// else — the double sin/cos, the three double quotients with their cancellation, the float rotation and translation
+// blocks — is the reference's formula, operation by operation (utilities.h:84-145).
+__device__ __forceinline__ void se3_exp_f(float* G, const float* p) {
+  const float ra1 = p[3] * p[3];
+  const float ra2 = p[4] * p[4];
+  const float ra3 = p[5] * p[5];
+  const float sig = sqrtf(ra1 + ra2 + ra3);
+  float sa, sb, sc;
+  const float sigsq2 = (sig * sig);
+  const float sigsq3 = (sig * sig * sig);
+  if ((double)sig > ICT_LIEALG_SIGTHRESH) {
+    double sn, cs;
+    sincos_small((double)sig, &sn, &cs);
+    sa = (float)(sn / (double)sig);
+    sb = (float)((1 - cs) / (double)sigsq2);
+    sc = (float)(((double)sig - sn) / (double)sigsq3);
+  } else {
+    sa = 1 - sigsq2 / 6 * (1 - sigsq2 / 20 * (1 - sigsq2 / 42));
+    sb = (float)(.5 * (double)(float)(1 - sigsq2 / 12 * (1 - sigsq2 / 30 * (1 - sigsq2 / 56))));
+    sc = (1 - sigsq2 / 20 * (1 - sigsq2 / 42 * (1 - sigsq2 / 72))) / 6;
+  }
+  float tmp1 = ra2 * sb;
+  float tmp2 = ra3 * sb;
+  float tmp3 = ra1 * sb;
+  float tmp4 = p[3] * p[4] * sb;
+  float tmp5 = p[5] * sa;
+  float tmp6 = p[3] * p[5] * sb;
+  float tmp7 = p[4] * sa;
+  float tmp8 = p[3] * sa;
+  float tmp9 = p[4] * p[5] * sb;
+  G[0] = 1 - tmp1 - tmp2;
+  G[1] = tmp4 - tmp5;
+  G[2] = tmp7 + tmp6;
+  G[4] = tmp5 + tmp4;
+  G[5] = 1 - tmp3 - tmp2;
+  G[6] = tmp9 - tmp8;
+  G[8] = tmp6 - tmp7;
+  G[9] = tmp8 + tmp9;
+  G[10] = 1 - tmp3 - tmp1;
+  tmp1 = p[5] * sb;
+  tmp2 = p[3] * p[4] * sc;
+  tmp3 = p[4] * sb;
+  tmp4 = p[3] * p[5] * sc;
+  tmp5 = p[3] * sb;
+  tmp6 = p[4] * p[5] * sc;
+  G[3] = (1 - (ra2 + ra3) * sc) * p[0] + (tmp2 - tmp1) * p[1] + (tmp3 + tmp4) * p[2];
+  G[7] = (tmp1 + tmp2) * p[0] + (1 - (ra1 + ra3) * sc) * p[1] + (tmp6 - tmp5) * p[2];
+  G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
+}
+
 // Production-kernel form of the float instantiation above.  sin(s)/s, (1-cos s)/s^2 and (s-sin s)/s^3 are even power
 // series in s; with z = s*s formed exactly in double from the float s they are evaluated by Horner in double (ten
 // terms: truncation < 1e-18 for s <= pi/4), so the three values narrowed to float equal the reference's
@@ -498,6 +553,44 @@ __device__ __forceinline__ void lu6_solve_exact(const Lu6& f, const float* b, fl
   } else c1 = 0.0f;
   c0 = rank > 0 ? c0 / LU(0, 0) : 0.0f;
   x[f.qd[0]] = c0; x[f.qd[1]] = c1; x[f.qd[2]] = c2; x[f.qd[3]] = c3; x[f.qd[4]] = c4; x[f.qd[5]] = c5;
+#undef LU
+}
+
+
+// lu6_solve_exact with the factors in registers (lu: column-major, uniform across the calling lanes) and the two
+// permutations applied through shared memory (b and x live there): same operations, same order, same bits.
+__device__ __forceinline__ void lu6_solve_regs(const float* lu, int rank, const int* pr, const int* qd, const float* b, float* x) {
+#define LU(i, j) lu[(i) + 6 * (j)]
+  float c0 = b[pr[0]], c1 = b[pr[1]], c2 = b[pr[2]], c3 = b[pr[3]], c4 = b[pr[4]], c5 = b[pr[5]];
+  if (rank == 0) c0 = c1 = c2 = c3 = c4 = c5 = 0.0f;
+  c1 = c1 - c0 * LU(1, 0); c2 = c2 - c0 * LU(2, 0); c3 = c3 - c0 * LU(3, 0); c4 = c4 - c0 * LU(4, 0); c5 = c5 - c0 * LU(5, 0);
+  c2 = c2 - c1 * LU(2, 1); c3 = c3 - c1 * LU(3, 1); c4 = c4 - c1 * LU(4, 1); c5 = c5 - c1 * LU(5, 1);
+  c3 = c3 - c2 * LU(3, 2); c4 = c4 - c2 * LU(4, 2); c5 = c5 - c2 * LU(5, 2);
+  c4 = c4 - c3 * LU(4, 3); c5 = c5 - c3 * LU(5, 3);
+  c5 = c5 - c4 * LU(5, 4);
+  if (rank > 5) {
+    c5 = c5 / LU(5, 5);
+    c0 = c0 - c5 * LU(0, 5); c1 = c1 - c5 * LU(1, 5); c2 = c2 - c5 * LU(2, 5); c3 = c3 - c5 * LU(3, 5); c4 = c4 - c5 * LU(4, 5);
+  } else c5 = 0.0f;
+  if (rank > 4) {
+    c4 = c4 / LU(4, 4);
+    c0 = c0 - c4 * LU(0, 4); c1 = c1 - c4 * LU(1, 4); c2 = c2 - c4 * LU(2, 4); c3 = c3 - c4 * LU(3, 4);
+  } else c4 = 0.0f;
+  if (rank > 3) {
+    c3 = c3 / LU(3, 3);
+    c0 = c0 - c3 * LU(0, 3); c1 = c1 - c3 * LU(1, 3); c2 = c2 - c3 * LU(2, 3);
+  } else c3 = 0.0f;
+  if (rank > 2) {
+    c2 = c2 / LU(2, 2);
+    c0 = c0 - c2 * LU(0, 2); c1 = c1 - c2 * LU(1, 2);
+  } else c2 = 0.0f;
+  if (rank > 1) {
+    c1 = c1 / LU(1, 1);
+    c0 = c0 - c1 * LU(0, 1);
+  } else c1 = 0.0f;
+  c0 = rank > 0 ? c0 / LU(0, 0) : 0.0f;
+  __syncwarp();
+  x[qd[0]] = c0; x[qd[1]] = c1; x[qd[2]] = c2; x[qd[3]] = c3; x[qd[4]] = c4; x[qd[5]] = c5;
 #undef LU
 }
 

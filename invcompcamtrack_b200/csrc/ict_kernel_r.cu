@@ -49,6 +49,7 @@ void count_launch_external();
 #define KR_WIN_BYTES (17 * KR_WROW * 4) /* one unit's window: 17 rows (row above + 16) */
 #define KR_SLOT_BYTES 2816              /* KR_WIN_BYTES rounded up to the 128-byte TMA destination alignment */
 #define KR_NSLOT 5
+
 #define KR_MAXU 16                      /* units per track: 2 per point, up to 8 points */
 #define KR_SD_BYTES_PER_POINT (6 * 1024 * 4)
 
@@ -58,6 +59,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
           ict_saddr(dst)),
       "l"(tmap), "r"(x), "r"(y), "r"(ict_saddr(bar))
       : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only(unsigned long long* b, unsigned bytes) {   // no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ict_saddr(b)), "r"(bytes) : "memory");
 }
 // generic-proxy accesses to shared memory (the in-place pdiff stores, the chain warps' loads) ordered before the
 // async-proxy write of the next TMA into the same slot
@@ -70,10 +74,11 @@ __device__ __forceinline__ void tmap_acquire(const void* tmap) {
 
 struct __align__(16) KrShared {
   unsigned long long win_full[KR_MAXU];    // unit's window landed (TMA complete_tx) or unit not visible: 1 arrival
-  unsigned long long pd_full[KR_MAXU];     // unit's pdiff rows written: the producer's 32 lanes arrive
-  unsigned long long slot_free[KR_MAXU];   // unit's pdiff consumed by both chain warps: 2 arrivals
-  unsigned long long gat_full;             // reference windows of a level landed
-  unsigned long long bsum;                 // chain warp B has published its two sums
+  unsigned long long slot_free[KR_MAXU];   // unit's pdiff consumed by its two chain warps: 2 arrivals
+  unsigned long long gat_full[2];          // reference windows of a level landed: points 0..3 / points 4..7
+  unsigned pd_flag[KR_MAXU];               // serial number of the iteration whose pdiff rows of the unit are written
+  unsigned b_flag;                         // ... in which chain warp B has published its two sums
+  unsigned pad_[3];
   float G[12];
   float p[8];
   float sum[8];
@@ -118,15 +123,51 @@ __device__ __forceinline__ void kr_sample16(const float* win, int lane, const fl
   }
 }
 
-// One unit of a chain: 16 rows, four elements per row, in the reference's order.
-__device__ __forceinline__ void kr_chain_unit(const float4* __restrict__ sd4, const float4* __restrict__ pd4, float& acc) {
+// Hand-offs that are on the critical path of an iteration are plain shared-memory flags (release store / acquire
+// load, ~30 cycles) instead of mbarriers (a try_wait costs ~90 cycles even when the phase is already complete); a
+// flag holds the serial number of the iteration it was last set in.
+__device__ __forceinline__ unsigned ld_acquire_s(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ict_saddr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ict_saddr(p)), "r"(v) : "memory");
+}
+
+// Eight rows of a chain: the 32 products first (independent), then the 32 additions in the reference's order.  Written
+// as two halves of a unit so that the loads and products of the second half sit in the shadow of the first half's
+// dependent additions (4 cycles each).
+struct KrRows8 {
+  float4 v[8];
+};
+// ptxas keeps only ~3 rows of loads in flight if left to itself, which does not cover the LDS.128 latency when four
+// chain warps and the producers share the SM's shared-memory pipe (measured: 35-45 cycles per row instead of 16).  The
+// loads are therefore volatile asm statements: they stay in program order, all sixteen of a half unit up front.
+__device__ __forceinline__ float4 lds128v(const float4* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ict_saddr(p)));
+  return v;
+}
+struct KrLoad8 {
+  float4 a[8], b[8];
+};
+__device__ __forceinline__ void kr_load8(const float4* a4, int astride, const float4* b4, int bstride, KrLoad8& o) {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const float4 s = sd4[r * 8], d = pd4[r * (KR_WROW / 4)];
-    acc = acc + s.x * d.x;
-    acc = acc + s.y * d.y;
-    acc = acc + s.z * d.z;
-    acc = acc + s.w * d.w;
+  for (int r = 0; r < 8; ++r) { o.a[r] = lds128v(a4 + r * astride); o.b[r] = lds128v(b4 + r * bstride); }
+}
+__device__ __forceinline__ void kr_mul8(const KrLoad8& l, KrRows8& o) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    o.v[r] = make_float4(l.a[r].x * l.b[r].x, l.a[r].y * l.b[r].y, l.a[r].z * l.b[r].z, l.a[r].w * l.b[r].w);
+}
+__device__ __forceinline__ void kr_add8(const KrRows8& p, float& acc) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    acc = acc + p.v[r].x;
+    acc = acc + p.v[r].y;
+    acc = acc + p.v[r].z;
+    acc = acc + p.v[r].w;
   }
 }
 
@@ -142,7 +183,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
   const int U = 2 * P;
   const bool donorm = op.donorm != 0;
 
-  // shared memory: [sd area: P x 24 KB][window slots: 6 x 2560][KrShared], 128-byte aligned for the TMA destinations
+  // shared memory: [sd area: P x 24 KB][window slots: 5 x 2816][KrShared], 128-byte aligned for the TMA destinations
   unsigned char* base = smem_raw + ((128u - (ict_saddr(smem_raw) & 127u)) & 127u);
   float* s_sd = reinterpret_cast<float*>(base);
   const int Pcap = prm.r_pcap;
@@ -155,7 +196,9 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
   const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
   const char* tm_ref = reinterpret_cast<const char*>(prm.frames[rf].tmap);
   const char* tm_new = reinterpret_cast<const char*>(prm.frames[nf].tmap);
-  const bool chainA = warp == 0, chainB = warp == 1, prod = warp >= 2;
+  // role 0: chain warp A (sums 0..3, lane = 8 k + c) and the serial section; role 1: chain warp B (sums 4, 5); the rest
+  // produce
+  const bool chainA = warp == 0, prod = warp >= 2;
   const int pw = warp - 2;
 
   // ---- ResetOdometer (odometer.cpp:580-609) + points -------------------------------------------------------------
@@ -174,12 +217,15 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
   if (tid >= 32 && tid < 32 + KR_MAXU) {
     mbar_init(&S.win_full[tid - 32], 1);
-    mbar_init(&S.pd_full[tid - 32], 32);
+    S.pd_flag[tid - 32] = 0u;
     mbar_init(&S.slot_free[tid - 32], 2);
+
   }
   if (tid == 64) {
-    mbar_init(&S.gat_full, 1);
-    mbar_init(&S.bsum, 1);
+    mbar_init(&S.gat_full[0], 1);
+    mbar_init(&S.gat_full[1], 1);
+    S.b_flag = 0u;
+
   }
   mbar_fence_init();
   __syncthreads();
@@ -290,28 +336,28 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     __syncthreads();
     // ---- 4b. reference windows: three TMA boxes per visible unit into the point's own sd area ---------------------
     if (warp == 0) {
-      int nvu = 0;
-      for (int u = 0; u < U; ++u) nvu += S.rvis[u >> 1];
-      if (lane == 0) {
-        if (nvu) mbar_expect_tx(&S.gat_full, 3u * KR_WIN_BYTES * nvu);
-        else mbar_arrive(&S.gat_full);
-      }
-      __syncwarp();
+      // every issuing lane adds its own 3 boxes to the transaction count of its barrier, lanes 0 and 1 then make the one
+      // arrival of each; two barriers, four points each, keep a barrier's pending transaction count below 64 KB
       if (lane < U && S.rvis[lane >> 1]) {
         const int pp = lane >> 1, half = lane & 1;
         unsigned char* dst = reinterpret_cast<unsigned char*>(s_sd) + (size_t)pp * KR_SD_BYTES_PER_POINT + half * 3 * KR_SLOT_BYTES;
         const int x = (S.rx[pp] - 1) & ~3, y = S.ry[pp] - 1 + 16 * half;
         fence_proxy_async();
-        tma_load_2d(dst, tmI, x, y, &S.gat_full);
-        tma_load_2d(dst + KR_SLOT_BYTES, tmDx, x, y, &S.gat_full);
-        tma_load_2d(dst + 2 * KR_SLOT_BYTES, tmDy, x, y, &S.gat_full);
+        unsigned long long* bar = &S.gat_full[pp >> 2];
+        mbar_expect_tx_only(bar, 3u * KR_WIN_BYTES);
+        tma_load_2d(dst, tmI, x, y, bar);
+        tma_load_2d(dst + KR_SLOT_BYTES, tmDx, x, y, bar);
+        tma_load_2d(dst + 2 * KR_SLOT_BYTES, tmDy, x, y, bar);
       }
+      __syncwarp();
+      if (lane < 2) mbar_arrive(&S.gat_full[lane]);
     }
     if (chainA && trace) lt1 = clock64();
     // ---- 4c/5. template gather (util_getPatch_grad, utilities.cpp:115-189) and steepest-descent values ------------
     float gx[UPP][16], gy[UPP][16];
     if (prod) {
-      mbar_wait(&S.gat_full, lvl & 1);
+      mbar_wait(&S.gat_full[0], lvl & 1);
+      mbar_wait(&S.gat_full[1], lvl & 1);
 #pragma unroll
       for (int s = 0; s < UPP; ++s) {
         const int u = pw + NPROD * s;
@@ -351,26 +397,61 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
 
     if (chainA && trace) lt2 = clock64();
     // ---- 6. Hessian: 21 reference-order sums, one chain per lane on six warps (odometer.cpp:428-472) ---------------
-    if (warp < 6) {
-      const int c = lane & 7, q = 4 * warp + (lane >> 3);
-      const int qa = kx_pair_a(q < 21 ? q : 20), qb = kx_pair_b(q < 21 ? q : 20);
-      const float4* A4 = reinterpret_cast<const float4*>(s_sd) + qa * 256 + c;
-      const float4* B4 = reinterpret_cast<const float4*>(s_sd) + qb * 256 + c;
-      float acc = -0.0f;   // -0 + x == x for every x: the chain starts with its first element (Eigen's redux)
-      for (int i = 0; i < P; ++i) {
-        const float4* a4 = A4 + i * 1536;
-        const float4* b4 = B4 + i * 1536;
+    // Three warps, three lane groups of eight chains (c = lane & 7) each; a group's sums share its sd planes, so a row
+    // costs eight LDS.128 for the 21 sums instead of twelve and no warp issues more than three of them (a warp gets a
+    // shared-memory load issued only every 7-10 cycles; an LDS.128 occupies the SM's pipe for four cycles whatever its
+    // lanes read), with one formula per warp (no selects, no divergence):
+    //   role 0, group g = 0..2, planes x = 2g, y = 2g + 1:                                 (x,x) (x,y) (y,y)
+    //   role 1, group g: plane pairs {0,1}x{2,3}, {0,1}x{4,5}, {2,3}x{4,5}, x = first of the left pair:  (x,z) (x,w)
+    //   role 2, the same groups, x = second of the left pair:                              (x,z) (x,w)
+    // Lanes 24..31 mirror group 2.
+    if (warp < 3) {
+      const int c = lane & 7, g = min(lane >> 3, 2);
+      auto qidx = [](int a, int b) { return a * 6 - (a * (a - 1)) / 2 + (b - a); };   // position in ComputeHessian's order
+      const float4* sd4 = reinterpret_cast<const float4*>(s_sd) + c;
+      if (warp == 0) {
+        const int px = 2 * g, py = 2 * g + 1;
+        const float4* X4 = sd4 + px * 256;
+        const float4* Y4 = sd4 + py * 256;
+        float a1 = -0.0f, a2 = -0.0f, a3 = -0.0f;   // -0 + x == x for every x: a chain starts with its first element
+        for (int i = 0; i < P; ++i) {
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const float4 a = a4[r * 8], b = b4[r * 8];
-          acc = acc + a.x * b.x;
-          acc = acc + a.y * b.y;
-          acc = acc + a.z * b.z;
-          acc = acc + a.w * b.w;
+          for (int r = 0; r < 32; ++r) {
+            const float4 x = X4[i * 1536 + r * 8], y = Y4[i * 1536 + r * 8];
+            a1 = a1 + x.x * x.x; a2 = a2 + x.x * y.x; a3 = a3 + y.x * y.x;
+            a1 = a1 + x.y * x.y; a2 = a2 + x.y * y.y; a3 = a3 + y.y * y.y;
+            a1 = a1 + x.z * x.z; a2 = a2 + x.z * y.z; a3 = a3 + y.z * y.z;
+            a1 = a1 + x.w * x.w; a2 = a2 + x.w * y.w; a3 = a3 + y.w * y.w;
+          }
+        }
+        const float r1 = kx_finish(a1), r2 = kx_finish(a2), r3 = kx_finish(a3);
+        if ((lane & 7) == 0 && lane < 24) {
+          S.Hsum[qidx(px, px)] = r1;
+          S.Hsum[qidx(px, py)] = r2;
+          S.Hsum[qidx(py, py)] = r3;
+        }
+      } else {
+        const int px = (g < 2 ? 0 : 2) + (warp - 1), pz = g == 0 ? 2 : 4;
+        const float4* X4 = sd4 + px * 256;
+        const float4* Z4 = sd4 + pz * 256;
+        const float4* W4 = Z4 + 256;
+        float a1 = -0.0f, a2 = -0.0f;
+        for (int i = 0; i < P; ++i) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float4 x = X4[i * 1536 + r * 8], z = Z4[i * 1536 + r * 8], w = W4[i * 1536 + r * 8];
+            a1 = a1 + x.x * z.x; a2 = a2 + x.x * w.x;
+            a1 = a1 + x.y * z.y; a2 = a2 + x.y * w.y;
+            a1 = a1 + x.z * z.z; a2 = a2 + x.z * w.z;
+            a1 = a1 + x.w * z.w; a2 = a2 + x.w * w.w;
+          }
+        }
+        const float r1 = kx_finish(a1), r2 = kx_finish(a2);
+        if ((lane & 7) == 0 && lane < 24) {
+          S.Hsum[qidx(px, pz)] = r1;
+          S.Hsum[qidx(px, pz + 1)] = r2;
         }
       }
-      const float res = kx_finish(acc);
-      if ((lane & 7) == 0 && q < 21) S.Hsum[q] = res;
     }
     fence_proxy_async();   // the sd coefficients in slot 0, before the first window lands there
     __syncthreads();
@@ -378,6 +459,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     if (chainA && trace) lt3 = clock64();
     if (chainA) {
       lu6_factor_warp(S.Hsum, S.f);
+
       normdp_init = 1e-10f;              // odometer.cpp:341-342
       const int cont0 = (0 < op.maxiter) & ((1e-10f / 1e-10f) > op.normdp_ratio);
       if (lane == 0) {
@@ -419,65 +501,99 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
               const float4 w = S.npl[pp];
               const float* wsh = win + ((S.nx[pp] - 1) & 3);   // the patch's left neighbour column inside the box
               mbar_wait(&S.win_full[u], par);
-              float a0 = wsh[lane + 1], b0 = wsh[lane];
+              // The residual rows go back INTO the window (row r of the patch over row r of the window, which only the
+              // sample of row r reads), at other word positions than the lanes read: every lane first loads all it
+              // needs, the warp synchronises, then it stores — lanes of a warp are not guaranteed to run in lockstep
+              // (they leave the barrier wait above one by one), and a lane that stored early would be sampled by its
+              // neighbours.
+              float a[17], b[17];
+#pragma unroll
+              for (int r = 0; r < 17; ++r) {
+                a[r] = wsh[r * KR_WROW + lane + 1];
+                b[r] = wsh[r * KR_WROW + lane];
+              }
+              __syncwarp();
 #pragma unroll
               for (int r = 0; r < 16; ++r) {
-                const float a1 = wsh[(r + 1) * KR_WROW + lane + 1], b1 = wsh[(r + 1) * KR_WROW + lane];
-                const float pn = ((w.x * a1 + w.y * b1) + w.z * a0) + w.w * b0;
+                const float pn = ((w.x * a[r + 1] + w.y * b[r + 1]) + w.z * a[r]) + w.w * b[r];
                 win[r * KR_WROW + perm] = refv[s][r] - pn;      // pdiff, odometer.cpp:381
-                a0 = a1;
-                b0 = b1;
               }
             } else {
 #pragma unroll
               for (int r = 0; r < 16; ++r) win[r * KR_WROW + perm] = 0.0f;   // sd_proj stays zero (odometer.cpp:352-357)
             }
             fence_proxy_async();          // the next write to this slot is a TMA (async proxy)
-            mbar_arrive(&S.pd_full[u]);
+            __syncwarp();
+            if (lane == 0) st_release_s(&S.pd_flag[u], gi + 1u);
           }
         }
       } else {
         // 9a. the 48 chains of J^T r: lane (k, c) adds sd_k * pdiff over its columns c, c+8, c+16, c+24 of every row
+        // (chain warp A: k = 0..3; chain warp B: k = 4, 5, its upper half mirrors the lower).  What bounds this loop is not
+        // the four dependent additions per row (16 cycles) but the two LDS.128 that feed them: a warp gets a
+        // shared-memory load issued only every 7-10 cycles (profiles/tools/probe/lds_probe2.cu), which with the loads'
+        // latency comes to 35-45 cycles per row.  One warp for all 48 chains (three loads per row) and four warps taking
+        // turns unit by unit were both measured slower than this split.
         const int c = lane & 7;
         const int k = chainA ? (lane >> 3) : 4 + ((lane >> 3) & 1);
         const float4* sdk = reinterpret_cast<const float4*>(s_sd) + k * 256 + c;
-        float acc = -0.0f;
-        long long t_c0 = 0, t_c1 = 0;
+        float acc = -0.0f;   // -0 + x == x for every x: the chain starts with its first element (Eigen's redux)
+        long long t_c0 = 0, t_c1 = 0, w0 = 0;   // instrumentation (chain warp A, trace only)
+        const unsigned want = gi + 1u;
         if (chainA && trace) t_c0 = clock64();
-        long long w0 = 0, w1 = 0, w2 = 0;   // instrumentation: cycles waiting for unit 0, units 1..3, later units
+        while (ld_acquire_s(&S.pd_flag[0]) != want) {}
+        if (chainA && trace) w0 = clock64() - t_c0;
+#pragma unroll 1
         for (int u = 0; u < U; ++u) {
           const float4* pd4 = reinterpret_cast<const float4*>(s_slots + (u % KR_NSLOT) * KR_SLOT_BYTES) + c;
-          const long long ta = (chainA && trace) ? clock64() : 0;
-          mbar_wait(&S.pd_full[u], par);
-          if (chainA && trace) {
-            const long long d = clock64() - ta;
-            if (u == 0) w0 += d; else if (u < 4) w1 += d; else w2 += d;
+          const float4* sd4 = sdk + (u >> 1) * 1536 + (u & 1) * 128;
+          unsigned nf = want;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 sv[8], dv[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              sv[r] = sd4[(8 * h + r) * 8];
+              dv[r] = pd4[(8 * h + r) * (KR_WROW / 4)];
+            }
+            if (h == 1 && u + 1 < U) nf = ld_acquire_s(&S.pd_flag[u + 1]);   // looked at early, needed after the additions
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              acc = acc + sv[r].x * dv[r].x;   // sd_k_proj, odometer.cpp:386-391, added in the order of .sum() (:399-404)
+              acc = acc + sv[r].y * dv[r].y;
+              acc = acc + sv[r].z * dv[r].z;
+              acc = acc + sv[r].w * dv[r].w;
+            }
           }
-          kr_chain_unit(sdk + (u >> 1) * 1536 + (u & 1) * 128, pd4, acc);
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.slot_free[u]);
+          while (nf != want) nf = ld_acquire_s(&S.pd_flag[u + 1]);
         }
-        if (chainA && trace) t_c1 = clock64();
         const float res = kx_finish(acc);   // Eigen's redux of the eight chains
-        if (chainB) {
+        if (!chainA) {
           if ((lane & 7) == 0 && lane < 16) S.sum[4 + (lane >> 3)] = res;
           __syncwarp();
-          if (lane == 0) mbar_arrive(&S.bsum);
+          if (lane == 0) st_release_s(&S.b_flag, want);
         } else {
           if ((lane & 7) == 0) S.sum[lane >> 3] = res;
-          mbar_wait(&S.bsum, par);
+          float lu[36];                   // the level's LU factors (column-major), every lane alike
+#pragma unroll
+          for (int j = 0; j < 36; ++j) lu[j] = S.f.lu[j];
+          const int lu_rank = S.f.rank;
+          while (ld_acquire_s(&S.b_flag) != want) {}
+          if (trace) t_c1 = clock64();
           __syncwarp();
-          // 9b. solve (odometer.cpp:407, Eigen's substitution order), 10. addpose_se3, stop rule — every lane alike
+          // 9b. solve (odometer.cpp:407, Eigen's substitution order), 10. addpose_se3, stop rule — every lane alike,
+          // operands in registers
           float sumsd[6], dp[6], pr[6], Gr[12];
 #pragma unroll
           for (int j = 0; j < 6; ++j) sumsd[j] = S.sum[j];
-          __syncwarp();
-          if (lane == 0) lu6_solve_exact(S.f, S.sum, S.dp);
+          lu6_solve_regs(lu, lu_rank, S.f.pr, S.f.qd, S.sum, S.dp);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 6; ++j) { dp[j] = S.dp[j]; pr[j] = S.p[j] + dp[j]; }
           Gr[3] = Gr[7] = Gr[11] = 0.0f;
-          se3_exp<float>(Gr, pr);
+          se3_exp_f(Gr, pr);
           const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
                                (fabsf(dp[4]) + fabsf(dp[5]));           // lpNorm<1>, odometer.cpp:412
           __syncwarp();
@@ -496,13 +612,11 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
               rec[15] = (float)S.nv;
               for (int j = 16; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
               rec[16] = (float)w0;
-              rec[17] = (float)w1;
-              rec[18] = (float)w2;
               if (it == 0) {   // first record of a level: cycles of its precompute phases
                 rec[19] = (float)(lt1 - lt0);   // acquires, reference placement, window issue
                 rec[20] = (float)(lt2 - lt1);   // window wait, sampling, sd store
                 rec[21] = (float)(lt3 - lt2);   // Hessian
-                rec[18] = (float)(lt4 - lt3);   // factorisation + first placement (replaces w2 in this record)
+                rec[18] = (float)(lt4 - lt3);   // factorisation + first placement
               }
               rec[22] = (float)(clock64() - t_c1);   // cycles of the serial section so far (finish, solve, exp)
               rec[23] = (float)(t_c1 - t_c0);        // cycles of the chain loop
