@@ -109,14 +109,25 @@ void ict_tracker_destroy(ict_tracker* tr);
 int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
 
 /* Order of the fp32 reductions (Hessian, J^T r, patch means):
- *   0 (default) fixed-order parallel tree — deterministic, fastest;
- *   1 the order of Eigen 3.3's vectorised .sum() with 4-float packets, which is what odometer.cpp:399-404,430-455 run
- *     (the model oracle/ictrack_oracle.c pins): results are then bit-identical to the oracle, about 3x slower.
- *   2 tree reductions with the general kernel (any psz / dopatchnorm) even where the specialised one applies —
+ *   1 (DEFAULT) the order of Eigen 3.3's vectorised .sum() with 4-float packets, which is what
+ *     odometer.cpp:399-404,430-455 run (the model oracle/ictrack_oracle.c pins): every iteration's J^T r and delta_p,
+ *     the iteration counts and the poses are bit-identical to the oracle — the mode that meets the parity gates
+ *     (identical iteration counts, J^T r and pose within 1e-5).
+ *   0 FAST MODE, opt-in: fixed-order parallel tree sums with the steepest-descent sums factorised per point —
+ *     deterministic, 3-4x faster, equal to the reference up to fp32 summation noise (first-iteration J^T r within 4e-7
+ *     of sum|sd*r|; later iterations diverge like the reference does from itself when its Eigen changes packet width:
+ *     ~90 % identical iteration counts on ill-conditioned 4-point tracks, 96 % on 100-point tracks).
+ *   2 tree reductions with the general kernel (any psz / dopatchnorm) even where a specialised one applies —
  *     for tests that compare the two kernels.
  * The multi-CTA path for oversized tracks honours 0 and 1 for the Hessian and J^T r (its patch means, only used with
  * dopatchnorm, are always warp trees). */
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
+
+/* Explicit switches of a tracker (tests and A/B tools; the library reads no environment variable in its default build):
+ *   "no_k2r"       1: reference-order 32x32 tracks run the producer/chain-ring kernel K2x even where K2r (resident
+ *                     steepest-descent images, TMA windows) applies — same bits, for comparisons
+ *   "seq_launches" 1: ict_track_sequence issues one launch per frame step even where one kernel could loop over the chain */
+int ict_tracker_set_knob(ict_tracker* tr, const char* name, int value);
 
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:
  *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ict_tracker_destroy": (None, [C.c_void_p]),
     "ict_tracker_set_optparam": (C.c_int, [C.c_void_p, C.POINTER(OptParam)]),
     "ict_tracker_set_sum_order": (C.c_int, [C.c_void_p, C.c_int]),
+    "ict_tracker_set_knob": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ict_tracker_set_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "ict_tracker_set_points_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_void_p]),
@@ -232,8 +233,12 @@ class Tracker:
         self.L = op.lv_f - op.lv_l + 1
 
     def set_sum_order(self, mode):
-        """0: fast fixed-order tree; 1: Eigen packet order (bit-identical to the oracle)."""
+        """1 (library default): Eigen packet order, bit-identical to the oracle; 0: fast mode (fixed-order tree sums)."""
         _check(lib().ict_tracker_set_sum_order(self.h_, int(mode)))
+
+    def set_knob(self, name, value):
+        """Explicit A/B switches: "no_k2r", "seq_launches" (ictrack.h)."""
+        _check(lib().ict_tracker_set_knob(self.h_, name.encode(), int(value)))
 
     def set_points(self, pt_off, pts, mutate_caller=False):
         """pt_off int64[T+1]; pts float64 [3*total]: per track X block, Y block, Z block."""

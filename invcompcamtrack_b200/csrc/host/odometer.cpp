@@ -32,7 +32,7 @@ void OdometerClass::SetSumOrder(int mode) {
 
 void OdometerClass::Set3Dpoints(double* pt_in, const int nopoints_in) {
   if (!tracker) return;
-  ict_tracker_set_optparam(tracker, op);   // the caller may have changed *op since construction
+  if (ict_tracker_set_optparam(tracker, op) != ICT_OK) report("Set3Dpoints: optparam");   // the caller may have changed *op since construction
   const int64_t off[2] = {0, nopoints_in};
   n_in = nopoints_in;
   nopoints = nopoints_in < op->maxpttrack ? nopoints_in : op->maxpttrack;
@@ -69,7 +69,7 @@ bool OdometerClass::bind_frame(int slot, const float** I, const float** dx, cons
 void OdometerClass::SetPose(const double* p_in, const float** img_ref_in, const float** img_ref_dx_in,
                             const float** img_ref_dy_in, const float** img_new_in) {
   if (!tracker || !view) return;
-  ict_tracker_set_optparam(tracker, op);
+  if (ict_tracker_set_optparam(tracker, op) != ICT_OK) report("optparam");
   for (int k = 0; k < 6; ++k) p_cur[k] = p_in[k];
   if (!bind_frame(0, img_ref_in, img_ref_dx_in, img_ref_dy_in) || !bind_frame(1, img_new_in, nullptr, nullptr))
     report("SetPose");
@@ -92,7 +92,7 @@ void OdometerClass::SetPose(const double* p_in, const float** img_ref_in, const 
 
 void OdometerClass::TrackPose(double* p_out) {
   if (!tracker || !view) return;
-  ict_tracker_set_optparam(tracker, op);
+  if (ict_tracker_set_optparam(tracker, op) != ICT_OK) report("optparam");
   const int rf = 0, nf = 1;
   if (ict_track_batch(tracker, view, &rf, &nf, p_cur, p_out, iters, nullptr, 0, nullptr) != ICT_OK) {
     report("TrackPose");

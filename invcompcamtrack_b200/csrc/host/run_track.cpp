@@ -8,7 +8,7 @@
 //   outfile (binary)                 6 f64 pose                                   (:83-97)
 //   images  binary PGM (P5) instead of whatever cv::imread accepts.
 // Written against the reference's class interface (CamClass / PoseClass / OdometerClass / util_constructpyramide);
-// the alignment itself runs on the GPU.  ICT_SUM_ORDER=1 selects the reference's summation order.
+// the alignment itself runs on the GPU.  The reference's summation order is the default; ICT_SUM_ORDER=0 selects the fast mode.
 #include <sys/time.h>
 
 #include <cstdint>

@@ -12,7 +12,7 @@
 // one NCC launch; only poses and correlations leave the device.  Two quirks of the reference are kept on purpose:
 // its NCC step sets op.dopatchnorm = true and never resets it (:281), so every sample after the first is TRACKED
 // with patch normalisation whatever the input file says; and Set3Dpoints runs once per sample, not per frame.
-// ICT_SUM_ORDER=1 selects the reference's summation order.
+// The reference's summation order is the default; ICT_SUM_ORDER=0 selects the fast mode.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -84,6 +84,7 @@ struct CopyLane {
     return e;
   }
   cudaError_t done(cudaStream_t user) {     // after the last kernel that reads the copied data
+    if (!s) return cudaSuccess;             // the lane never copied anything (points set by a blocking / device call)
     cudaError_t e = cudaEventRecord(consumed, user);
     have_consumed = e == cudaSuccess;
     return e;
@@ -459,18 +460,24 @@ struct ict_tracker {
   int max_pts = 0;
   std::vector<int64_t> h_off;
   bool have_2d = false;
-  int sum_mode = 0;
+  int sum_mode = 1;            // the reference's summation order is the default (ictrack.h, ict_tracker_set_sum_order)
   int force_general = 0;
+  int knob_no_k2r = 0, knob_seq_launches = 0;   // ict_tracker_set_knob
   int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
   const int *big_rf = nullptr, *big_nf = nullptr;   // set by ict_track_batch around run_tracks: per-track frames (host) of the multi-CTA path
-  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, ticket;
+  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
 };
 
+static bool optparam_ok(const ict_optparam* op) {
+  return op && op->psz >= 1 && op->lv_f >= op->lv_l && op->lv_l >= 0 && op->lv_f < ICT_MAX_LEVELS && op->maxpttrack >= 1 &&
+         op->maxiter >= 0;
+}
+
 ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2]) {
   if (require_device()) return nullptr;
-  if (!op || op->psz < 1 || op->lv_f < op->lv_l || op->lv_l < 0 || op->lv_f >= ICT_MAX_LEVELS || op->maxpttrack < 1) {
+  if (!optparam_ok(op) || !fc || !cc || !wh) {
     fail(ICT_ERR_BAD_ARG, "ict_tracker_create: bad optparam");
     return nullptr;
   }
@@ -486,7 +493,7 @@ ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const
 void ict_tracker_destroy(ict_tracker* tr) {
   if (!tr) return;
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
-                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->ticket};
+                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big};
   for (DevBuf* x : b) x->release();
   tr->lane.release();
   tr->lane_in.release();
@@ -497,12 +504,24 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op) {
   if (!tr || !op) return fail(ICT_ERR_BAD_ARG, "null argument");
   if (op->psz != tr->op.psz || op->lv_f != tr->op.lv_f)
     return fail(ICT_ERR_BAD_ARG, "psz and lv_f are fixed at creation (they size the camera and the pyramids)");
+  if (!optparam_ok(op)) return fail(ICT_ERR_BAD_ARG, "ict_tracker_set_optparam: bad optparam (lv_l, maxpttrack or maxiter out of range)");
   tr->op = *op;
+  tr->op.pszd2 = op->psz / 2;                      // the derived fields follow psz (run_io_reprojection_test.cpp:115-117)
+  tr->op.pszd2m3 = op->psz + op->psz / 2 - 1;
+  tr->op.novals = op->psz * op->psz;
+  return ICT_OK;
+}
+
+int ict_tracker_set_knob(ict_tracker* tr, const char* name, int value) {
+  if (!tr || !name) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (!strcmp(name, "no_k2r")) tr->knob_no_k2r = value ? 1 : 0;
+  else if (!strcmp(name, "seq_launches")) tr->knob_seq_launches = value ? 1 : 0;
+  else return fail(ICT_ERR_BAD_ARG, std::string("unknown knob: ") + name);
   return ICT_OK;
 }
 
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode) {
-  if (!tr || mode < 0 || mode > 2) return fail(ICT_ERR_BAD_ARG, "sum order must be 0 (tree), 1 (reference order) or 2");
+  if (!tr || mode < 0 || mode > 2) return fail(ICT_ERR_BAD_ARG, "sum order must be 1 (reference order, default), 0 (fast tree order) or 2");
   tr->sum_mode = mode == 1 ? 1 : 0;
   tr->force_general = mode == 2 ? 1 : 0;
   return ICT_OK;
@@ -621,19 +640,13 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.force_general = tr->force_general;
   prm.seq_n = tr->seq_n;
   prm.seq_step = tr->seq_step;
-  prm.dbg_skip_serial = getenv("ICT_DBG_SKIP_SERIAL") ? atoi(getenv("ICT_DBG_SKIP_SERIAL")) : 0;
-  prm.serial_warp_last = getenv("ICT_SERIAL_WARP_LAST") ? 1 : 0;
-  prm.v2_lu_setup = getenv("ICT_V2_LU") ? 1 : 0;
-  // K2p (two slots per persistent CTA, ict_kernel_pipe.cu) measured 2.67e11 against 3.2e11 pixel-residuals/s for one
-  // track per CTA on B200; it stays selectable for experiments and is covered by a parity test.
-  const int use_pipe = getenv("ICT_PIPE") ? 1 : 0;
-  const bool pipe_ok = use_pipe && !tr->sum_mode && !tr->force_general && !tr->op.dopatchnorm &&
-                       (tr->op.psz == 8 || tr->op.psz == 16 || tr->op.psz == 32) &&
-                       pipe_smem_bytes(tr->op, tr->max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT;
-  if (pipe_ok) {
-    CU(tr->ticket.reserve(sizeof(int)));
-    CU(launch_track_pipe(prm, tr->max_pts, tr->ticket.as<int>(), st));
-  } else if (track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general)) {
+  prm.knob_no_k2r = tr->knob_no_k2r;
+  prm.knob_seq_launches = tr->knob_seq_launches;
+  // profiling builds only (ict_knobs.h): these change what the kernels compute or where their serial sections run
+  prm.dbg_skip_serial = ict_knob("ICT_DBG_SKIP_SERIAL") ? atoi(ict_knob("ICT_DBG_SKIP_SERIAL")) : 0;
+  prm.serial_warp_last = ict_knob("ICT_SERIAL_WARP_LAST") ? 1 : 0;
+  prm.v2_lu_setup = ict_knob("ICT_V2_LU") ? 1 : 0;
+  if (track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general)) {
     CU(launch_track(prm, tr->max_pts, st));
   } else {
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
@@ -716,6 +729,9 @@ int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref
   if (T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
   if (!track_fits_one_cta(tr->op, tr->max_pts, tr->sum_mode, tr->force_general))
     return fail(ICT_ERR_UNSUPPORTED, "stream variant handles tracks that fit one CTA");
+  for (int t = 0; t < T; ++t)
+    if (ref_frame[t] < 0 || ref_frame[t] >= fs->nframes || new_frame[t] < 0 || new_frame[t] >= fs->nframes)
+      return fail(ICT_ERR_BAD_ARG, "frame index out of range");
   const int L = tr->op.lv_f - tr->op.lv_l + 1;
   CU(tr->rf.reserve(sizeof(int) * (size_t)T));
   CU(tr->nf.reserve(sizeof(int) * (size_t)T));
@@ -755,7 +771,7 @@ int ict_track_sequence(ict_tracker* tr, const ict_frames* fs, int first, int nst
   CU(tr->npix.reserve(sizeof(long long) * (size_t)T * (nsteps ? nsteps : 1)));
   double* chain = tr->p_out.as<double>();
   CU(cudaMemcpyAsync(chain, p_in, sizeof(double) * 6 * (size_t)T, cudaMemcpyHostToDevice, 0));
-  if (nsteps > 1 && track_chain_in_one_launch(tr->op, tr->max_pts, tr->sum_mode, tr->force_general)) {
+  if (nsteps > 1 && track_chain_in_one_launch(tr->op, tr->max_pts, tr->sum_mode, tr->force_general, tr->knob_seq_launches)) {
     // K2v8 loops over the frames inside the kernel: one launch for the whole chain
     tr->seq_n = nsteps;
     tr->seq_step = step;
@@ -833,25 +849,29 @@ int ict_ncc_score(ict_tracker* tr, const ict_frames* fs, int frame_b, int frame_
                   const float* pt2d_back, const float* pt2d_refe, const float* pt2d_forw, float* out_corr) {
   if (!tr || !fs || !pt2d_back || !pt2d_refe || !pt2d_forw || !out_corr) return fail(ICT_ERR_BAD_ARG, "null argument");
   if (tr->T <= 0 || tr->h_off.empty()) return fail(ICT_ERR_BAD_ARG, "no points set");
+  if (fs->view || !fs->I) return fail(ICT_ERR_BAD_ARG, "ict_ncc_score: needs a store that owns its pixels (not a view)");
+  if (fs->lv_f != tr->op.lv_f || fs->pad != tr->op.psz || fs->w != tr->wh[0] || fs->h != tr->wh[1])
+    return fail(ICT_ERR_BAD_ARG, "frame store does not match the tracker (need lv_f, pad == psz, w, h equal)");
+  if (nback < 0 || nfwd < 0 || nback + nfwd == 0) return fail(ICT_ERR_BAD_ARG, "ict_ncc_score: nback + nfwd must be positive");
   if (frames_range_ok(fs, frame_b, 1) || frames_range_ok(fs, frame_r, 1) || frames_range_ok(fs, frame_f, 1))
     return ICT_ERR_BAD_ARG;
   const size_t total = (size_t)tr->total;
   DevBuf in, out;
-  CU(in.reserve(sizeof(float) * 6 * total));
-  CU(out.reserve(sizeof(float) * total));
+  int rc = ICT_OK;
+  cudaError_t e = in.reserve(sizeof(float) * 6 * total);
+  if (e == cudaSuccess) e = out.reserve(sizeof(float) * total);
   float* d = in.as<float>();
-  CU(cudaMemcpyAsync(d, pt2d_back, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
-  CU(cudaMemcpyAsync(d + 2 * total, pt2d_refe, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
-  CU(cudaMemcpyAsync(d + 4 * total, pt2d_forw, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d, pt2d_back, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * total, pt2d_refe, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 4 * total, pt2d_forw, sizeof(float) * 2 * total, cudaMemcpyHostToDevice, 0);
   const int l = tr->op.lv_l;
   const size_t fo = (size_t)fs->plane_floats;
-  cudaError_t e = launch_ncc(tr->op, tr->cam, fs->I + frame_b * fo + fs->level_off[l], fs->I + frame_r * fo + fs->level_off[l],
-                             fs->I + frame_f * fo + fs->level_off[l], nback, nfwd, tr->pt_off.as<int64_t>(), tr->T, d,
-                             d + 2 * total, d + 4 * total, out.as<float>(), 0);
-  int rc = ICT_OK;
-  if (e != cudaSuccess) rc = fail(ICT_ERR_CUDA, std::string("launch_ncc: ") + cudaGetErrorString(e));
-  if (rc == ICT_OK && cudaMemcpy(out_corr, out.p, sizeof(float) * total, cudaMemcpyDeviceToHost) != cudaSuccess)
-    rc = fail(ICT_ERR_CUDA, "ncc download failed");
+  if (e == cudaSuccess)
+    e = launch_ncc(tr->op, tr->cam, fs->I + frame_b * fo + fs->level_off[l], fs->I + frame_r * fo + fs->level_off[l],
+                   fs->I + frame_f * fo + fs->level_off[l], nback, nfwd, tr->pt_off.as<int64_t>(), tr->T, d, d + 2 * total,
+                   d + 4 * total, out.as<float>(), 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out_corr, out.p, sizeof(float) * total, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) rc = fail(ICT_ERR_CUDA, std::string("ict_ncc_score: ") + cudaGetErrorString(e));
   in.release();
   out.release();
   return rc;

@@ -415,7 +415,7 @@ static cudaError_t launch_v2_t(const TrackParams& prm, size_t smem, cudaStream_t
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ICT_TRACK_SMEM_LIMIT);
-    const char* co = getenv("ICT_V2_CARVEOUT");      // profiling knob: shared-memory carve-out in percent
+    const char* co = ict_knob("ICT_V2_CARVEOUT");      // profiling knob: shared-memory carve-out in percent
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(k_track_v2<KT, MINB, TRACE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                co ? atoi(co) : 100);
@@ -433,15 +433,15 @@ cudaError_t launch_track_v2(const TrackParams& prm, int max_pts, cudaStream_t st
   if (smem > (size_t)ICT_TRACK_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
   static int variant = -1;
   if (variant < 0) {
-    const char* e = getenv("ICT_V2_VARIANT");       // tuning knob for profiling runs only
+    const char* e = ict_knob("ICT_V2_VARIANT");       // tuning knob for profiling runs only
     variant = e ? atoi(e) : 0;
   }
   // More points per track = more template per CTA = fewer CTAs per SM: keep ~32 warps per SM by giving the track more
   // warps (a warp still owns 16 rows of one point at a time; per-group sums make the result independent of it).
   const int P = max_pts < prm.op.maxpttrack ? max_pts : prm.op.maxpttrack;
-  if (P > 8 && !getenv("ICT_V2_256"))
+  if (P > 8 && !ict_knob("ICT_V2_256"))
     return prm.trace ? launch_v2_t<16, 1, true, 1024>(prm, smem, stream) : launch_v2_t<16, 1, false, 1024>(prm, smem, stream);
-  if (P > 4 && !getenv("ICT_V2_256"))
+  if (P > 4 && !ict_knob("ICT_V2_256"))
     return prm.trace ? launch_v2_t<16, 2, true, 512>(prm, smem, stream) : launch_v2_t<16, 2, false, 512>(prm, smem, stream);
   if (prm.trace) return launch_v2_t<16, 4, true>(prm, smem, stream);   // same arithmetic + per-iteration records
   switch (variant) {

@@ -1182,7 +1182,7 @@ static cudaError_t launch_track_fast_t(const TrackParams& prm, size_t smem, int 
   // beat three even though 64 registers spill ~230 B in the per-level precompute.
   static int variant = -1;
   if (variant < 0) {
-    const char* e = getenv("ICT_FAST_VARIANT");   // tuning knob for profiling runs only
+    const char* e = ict_knob("ICT_FAST_VARIANT");   // tuning knob for profiling runs only
     variant = e ? atoi(e) : 4;
   }
   if (PSZ == 32) {
@@ -1238,20 +1238,20 @@ static cudaError_t launch_track_p(const TrackParams& prm, size_t smem, int nt, i
 bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int force_general) {
   if (track_smem_bytes(op, max_pts, sum_mode) <= (size_t)ICT_TRACK_SMEM_LIMIT) return true;
   if (force_general) return false;
-  if (sum_mode) return !getenv("ICT_EXACT_V1") && kx8_supported(op, max_pts);
-  return !getenv("ICT_FAST_V1") && v8_supported(op, max_pts);
+  if (sum_mode) return !ict_knob("ICT_EXACT_V1") && kx8_supported(op, max_pts);
+  return !ict_knob("ICT_FAST_V1") && v8_supported(op, max_pts);
 }
 
 // True when launch_track runs K2v8 for this configuration: the kernel that can take a whole chain of frame steps
 // (TrackParams.seq_n) in one launch.
-bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general) {
-  return sum_mode == 0 && !force_general && !getenv("ICT_FAST_V1") && !getenv("ICT_PIPE") && !getenv("ICT_SEQ_LAUNCHES") &&
+bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general, int per_frame_launches) {
+  return sum_mode == 0 && !force_general && !per_frame_launches && !ict_knob("ICT_FAST_V1") &&
          v8_supported(op, max_pts);
 }
 
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
-  if (prm.seq_n > 1 && !track_chain_in_one_launch(prm.op, max_pts, prm.sum_mode, prm.force_general))
+  if (prm.seq_n > 1 && !track_chain_in_one_launch(prm.op, max_pts, prm.sum_mode, prm.force_general, prm.knob_seq_launches))
     return cudaErrorInvalidConfiguration;   // only K2v8 loops over frames
   const size_t smem = track_smem_bytes(prm.op, max_pts, prm.sum_mode);
   if (!track_fits_one_cta(prm.op, max_pts, prm.sum_mode, prm.force_general)) return cudaErrorInvalidConfiguration;
@@ -1259,10 +1259,10 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
   const long long E = (long long)P * prm.op.novals;
   int nt = E >= 2048 ? 256 : (E >= 512 ? 128 : 64);
   const int mode = (prm.op.dopatchnorm ? 1 : 0) | (prm.sum_mode ? 2 : 0);
-  if (const char* e = getenv("ICT_NT")) nt = atoi(e);   // profiling knob
-  if ((mode & 2) == 0 && !prm.force_general && !getenv("ICT_FAST_V1") && v8_supported(prm.op, max_pts))
+  if (const char* e = ict_knob("ICT_NT")) nt = atoi(e);   // profiling knob
+  if ((mode & 2) == 0 && !prm.force_general && !ict_knob("ICT_FAST_V1") && v8_supported(prm.op, max_pts))
     return launch_track_v8(prm, max_pts, stream);      // K2v8: 8x8 patches, with or without dopatchnorm
-  if (mode == 0 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_FAST_V1") &&
+  if (mode == 0 && !prm.force_general && prm.op.psz == 32 && !ict_knob("ICT_FAST_V1") &&
       v2_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
     return launch_track_v2(prm, max_pts, stream);
   if (mode == 0 && !prm.force_general && (prm.op.psz == 8 || prm.op.psz == 16 || prm.op.psz == 32)) {
@@ -1273,12 +1273,12 @@ cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t strea
       default: return launch_track_fast_t<32>(prm, fsm, nt, stream);
     }
   }
-  if ((mode & 2) && !prm.force_general && !getenv("ICT_EXACT_V1") && kx8_supported(prm.op, max_pts))
+  if ((mode & 2) && !prm.force_general && !ict_knob("ICT_EXACT_V1") && kx8_supported(prm.op, max_pts))
     return launch_track_x8(prm, max_pts, stream);      // K2x8: reference-order sums, 8x8 patches, +/- dopatchnorm
-  if (mode == 2 && !prm.force_general && !getenv("ICT_EXACT_V1") && !getenv("ICT_EXACT_X") &&
+  if (mode == 2 && !prm.force_general && !prm.knob_no_k2r && !ict_knob("ICT_EXACT_V1") &&
       kr_supported(prm.op, max_pts, prm.tma_ok))
     return launch_track_r(prm, max_pts, stream);       // K2r: reference-order sums, resident sd images, TMA windows
-  if (mode == 2 && !prm.force_general && prm.op.psz == 32 && !getenv("ICT_EXACT_V1") &&
+  if (mode == 2 && !prm.force_general && prm.op.psz == 32 && !ict_knob("ICT_EXACT_V1") &&
       kx_smem_bytes(prm.op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT)
     return launch_track_x(prm, max_pts, stream);       // K2x: reference-order sums, producer/chain warps
   const int ntx = (mode & 2) && nt < 192 ? 192 : nt;   // the reference-order Hessian needs 21*8 = 168 threads

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/ictrack.h"
+#include "ict_knobs.h"
 
 namespace ict {
 
@@ -49,6 +50,8 @@ struct TrackParams {
   int seq_n, seq_step;             // K2v8 only: seq_n > 1 runs a whole chain in one launch — step k tracks frame
                                    //    fixed_ref + k*seq_step -> + seq_step from pose p_in + 6*T*k to p_out + 6*T*k
                                    //    (iters + T*L*k, npixres + T*k); 0/1: a single step
+  int knob_no_k2r;                 // tracker knob "no_k2r": reference-order psz 32 runs K2x even where K2r applies (A/B, tests)
+  int knob_seq_launches;           // tracker knob "seq_launches": a chain is one launch per frame step even where K2v8 could loop
   int tma_ok;                      // every frame of the store carries tensor maps (FrameDesc.tmap)
   int r_pcap;                      // K2r: points per track the shared-memory layout is sized for (set by its launcher)
   int sum_mode;                    // 0: fixed-order tree reductions (fast); 1: Eigen-3.3 packet order (bit-exact
@@ -71,7 +74,7 @@ cudaError_t launch_set_points(int T, const int64_t* pt_off, const double* pts, d
 // Returns cudaErrorInvalidConfiguration when a track does not fit (caller then uses the multi-CTA path).
 size_t track_smem_bytes(const ict_optparam& op, int max_pts, int sum_mode);
 bool track_fits_one_cta(const ict_optparam& op, int max_pts, int sum_mode, int force_general);
-bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general);
+bool track_chain_in_one_launch(const ict_optparam& op, int max_pts, int sum_mode, int force_general, int per_frame_launches);
 cudaError_t launch_track(const TrackParams& prm, int max_pts, cudaStream_t stream);
 
 // K2v2 (ict_kernel_v2.cu): the production kernel for psz 32 without dopatchnorm, tree sums; launch_track routes
@@ -102,11 +105,6 @@ cudaError_t launch_track_r(const TrackParams& prm, int max_pts, cudaStream_t str
 bool kx8_supported(const ict_optparam& op, int max_pts);
 size_t kx8_smem_bytes(const ict_optparam& op, int max_pts);
 cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t stream);
-
-// K2p: two track slots per persistent CTA, serial steps of one slot overlapped with pixel steps of the other.
-// ticket: one device int (zeroed by the launch).  Handles psz 8/16/32 without dopatchnorm, tree sums.
-size_t pipe_smem_bytes(const ict_optparam& op, int max_pts);
-cudaError_t launch_track_pipe(const TrackParams& prm, int max_pts, int* ticket, cudaStream_t stream);
 
 // SetPose only: setpose_se3 + reprojection at lv_l into prm.pt2d_out (one CTA per track)
 cudaError_t launch_reproject(const TrackParams& prm, cudaStream_t stream);

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(192) k_big_level_hessian_exact(const BigArgs a
   if (tid < 21 * 8) {
     int x = 0, y = 0;
     pair_of(tid >> 3, x, y);
-    s_chain[tid] = eigen_chain([&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, tid & 7, as2, E);
+    s_chain[tid] = eigen_chain_prefetch([&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, tid & 7, as2, E);
   }
   __syncthreads();
   if (tid < 21) {
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(64) k_big_iter_sums_exact(const BigArgs a) {
   __shared__ float s_chain[6 * 8];
   const int tid = threadIdx.x;
   const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E, as2 = (Nfull / 8) * 8;
-  if (tid < 48) s_chain[tid] = eigen_chain([&](int e) { return big_sd_at(a, tid >> 3, e) * a.w.pnew[e]; }, tid & 7, as2, E);
+  if (tid < 48) s_chain[tid] = eigen_chain_prefetch([&](int e) { return big_sd_at(a, tid >> 3, e) * a.w.pnew[e]; }, tid & 7, as2, E);
   __syncthreads();
   if (tid < 6)   // the finishing kernel reads partials as part[cta*21 + k] with ncta CTAs: publish as CTA 0 of 1
     a.w.part[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, tid, e) * a.w.pnew[e]; }, Nfull, E);
@@ -827,22 +827,27 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   a.E = (long long)a.P * prm.op.novals;
   const ict_optparam& op = prm.op;
   const int ncta = a.w.ncta;
-  const int pcta = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
+  const int pcta_ = (int)((a.P + 255) / 256 < 148 * 8 ? (a.P + 255) / 256 : 148 * 8);
+  const int pcta = pcta_ > 0 ? pcta_ : 1;   // an empty track still runs the launch chain (its sums are empty, its pose unchanged)
   const bool pn = op.dopatchnorm != 0;
   const bool ex = prm.sum_mode != 0;   // reference-order sums
-  const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !getenv("ICT_DENSE_V1");
+  const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !ict_knob("ICT_DENSE_V1");
   int nl = 0;
   k_big_init<<<ncta, 256, 0, st>>>(a, fused ? 1 : 0); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
   for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
     // bulk-copy staging needs 16-byte aligned streams: point counts and the track's offset multiples of four
-    const bool tma = t == 0 && (a.P % 4 == 0) && (a.n_in % 4 == 0) && !getenv("ICT_DENSE_LDG");   // t == 0: offset 0
-    static int nst = 0, pdl = 1;
-    if (!nst) {
-      nst = getenv("ICT_DENSE_NST") ? atoi(getenv("ICT_DENSE_NST")) : 3;     // A/B knobs
-      pdl = getenv("ICT_DENSE_NOPDL") ? 0 : 1;
-      cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 10240);
-      cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    const bool tma = t == 0 && (a.P % 4 == 0) && (a.n_in % 4 == 0) && !ict_knob("ICT_DENSE_LDG");   // t == 0: offset 0
+    const int nst = ict_knob("ICT_DENSE_NST") ? atoi(ict_knob("ICT_DENSE_NST")) : 3;     // A/B knobs (profiling builds)
+    const int pdl = ict_knob("ICT_DENSE_NOPDL") ? 0 : 1;
+    static bool attr_dev[64] = {};            // function attributes are per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_dev[dev_ & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 10240);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dense_iter_tma<5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+      attr_dev[dev_ & 63] = true;
     }
     // programmatic dependent launch: iteration k+1 becomes resident while the last CTA of iteration k still runs the
     // solve, and its first tiles are in flight by the time the pose is published
@@ -1000,11 +1005,13 @@ cudaError_t launch_ncc(const ict_optparam& op, const CamLevels& cam, const float
   if (total <= 0) return cudaSuccess;
   const size_t smem = sizeof(float) * 3 * (size_t)op.novals;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr_dev[64] = {};              // function attributes are per device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  if (!attr_dev[dev_ & 63]) {
     e = cudaFuncSetAttribute(k_ncc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_dev[dev_ & 63] = true;
   }
   k_ncc<<<(unsigned)total, 128, smem, stream>>>(op, cam, img_b, img_r, img_f, nback, nfwd, pt_off, T, pb, pr, pf, out);
   count_launch_external();

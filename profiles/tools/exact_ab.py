@@ -1,5 +1,5 @@
 """A/B of the reference-order kernels on C3-geometry tracks (4 points of 32x32 per track, 1080p pair):
-K2r (default route of sum_order 1), K2x (ICT_EXACT_X=1) and, for scale, K2v2 (sum_order 0).
+K2r (default route of sum_order 1), K2x (tracker knob "no_k2r") and, for scale, K2v2 (sum_order 0).
 Checks K2r against the oracle on the first NCHK tracks, then times ict_track_batch (host call, median of REPS).
 
     python profiles/tools/exact_ab.py [ntracks] [npts]
@@ -25,11 +25,8 @@ tr.set_points(c["pt_off"], c["pts"].copy())
 p_in = np.zeros((NT, 6))
 
 
-def run(order, env=None, trace_cap=0):
-    for k in ("ICT_EXACT_X",):
-        os.environ.pop(k, None)
-    if env:
-        os.environ[env] = "1"
+def run(order, knob=None, trace_cap=0):
+    tr.set_knob("no_k2r", 1 if knob else 0)
     tr.set_sum_order(order)
     ts = []
     out = None
@@ -50,8 +47,8 @@ gs = {k: (v[:NCHK] if v is not None else None) for k, v in g.items()}
 assert_bit_identical(gs, o)
 print("K2r bit-identical to the oracle on %d tracks (trace, iters, npixres, poses)" % NCHK, flush=True)
 res = {}
-for name, order, env in (("K2r", 1, None), ("K2x", 1, "ICT_EXACT_X"), ("K2v2", 0, None)):
-    out, dt = run(order, env)
+for name, order, knob in (("K2r", 1, None), ("K2x", 1, "no_k2r"), ("K2v2", 0, None)):
+    out, dt = run(order, knob)
     res[name] = out
     npx = int(out["npixres"].sum())
     print("%-5s %8.3f ms  %.3e pixel-residuals/s  %.3e tracks/s  iters/track %.1f" %

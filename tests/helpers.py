@@ -42,12 +42,15 @@ def oracle_run(orc, case, trace_cap=64, sum_mode=0, nthreads=0, p_in=None):
 
 
 def gpu_run(ict, case, trace_cap=64, p_in=None, sum_order=0):
+    """sum_order 0 = the opt-in fast mode (tree sums), 1 = the library default (reference order), None = leave the
+    library default untouched."""
     c = case
     op = ict.OptParam.from_buffer_copy(bytes(c["op"]))
     fr = ict.Frames(2, c["w"], c["h"], c["lv_f"], c["psz"])
     fr.upload(0, np.stack([c["A"], c["B"]]))
     tr = ict.Tracker(op, c["sc"].fc, c["sc"].cc, c["sc"].wh)
-    tr.set_sum_order(sum_order)
+    if sum_order is not None:
+        tr.set_sum_order(sum_order)
     pts = c["pts"].copy()
     tr.set_points(c["pt_off"], pts)
     T = c["T"]

@@ -184,10 +184,9 @@ def test_sequence_chain(ict, orc):
 
 @pytest.mark.parametrize("kw", [dict(npts=60, S=7), dict(npts=150, S=3, donorm=1, dopatchnorm=1)])
 def test_chain_in_one_launch_equals_per_frame_launches(ict, kw):
-    """ict_track_sequence with psz 8 in the default order: K2v8 loops over the frames inside ONE launch (a track's step
+    """ict_track_sequence with psz 8 in the fast mode: K2v8 loops over the frames inside ONE launch (a track's step
     k+1 depends on its own step k only).  Same poses, iteration counts and pixel-residual counts, bit for bit, as one
-    launch per frame (ICT_SEQ_LAUNCHES=1), forwards and backwards."""
-    import os
+    launch per frame (tracker knob "seq_launches"), forwards and backwards."""
     from invcompcamtrack_b200 import synth
     nfr, S, n = 6, kw["S"], kw["npts"]
     sc, frames, poses = synth.make_sequence(3, nfr, 320, 240)
@@ -195,18 +194,15 @@ def test_chain_in_one_launch_equals_per_frame_launches(ict, kw):
     fr = ict.Frames(nfr, 320, 240, 2, 8)
     fr.upload(0, np.stack(frames))
     tr = ict.Tracker(op, sc.fc, sc.cc, sc.wh)
+    tr.set_sum_order(0)                              # the chain-in-one-launch kernel is the fast mode's K2v8
     tr.set_points(np.arange(S + 1, dtype=np.int64) * n, np.concatenate([sc.points(70 + s, n, 8, 2) for s in range(S)]))
     p0 = np.zeros((S, 6))
     p0[:, 3] = np.linspace(-0.01, 0.01, S)          # chains that start apart
-    try:
-        os.environ.pop("ICT_SEQ_LAUNCHES", None)
-        a = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
-        ab = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, a["poses"][-1])
-        os.environ["ICT_SEQ_LAUNCHES"] = "1"
-        b = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
-        bb = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, b["poses"][-1])
-    finally:
-        os.environ.pop("ICT_SEQ_LAUNCHES", None)
+    a = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
+    ab = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, a["poses"][-1])
+    tr.set_knob("seq_launches", 1)
+    b = tr.track_sequence(fr, 0, nfr - 1, 1, p0)
+    bb = tr.track_sequence(fr, nfr - 1, nfr - 1, -1, b["poses"][-1])
     for x, y in ((a, b), (ab, bb)):
         assert np.array_equal(x["poses"], y["poses"])
         assert np.array_equal(x["iters"], y["iters"]) and np.array_equal(x["npixres"], y["npixres"])
@@ -286,23 +282,6 @@ def test_ncc_scoring(ict, orc):
     assert np.abs(got - ref).max() < 2e-5
 
 
-def test_pipelined_kernel_variant(ict, orc, monkeypatch):
-    """ICT_PIPE=1 selects the software-pipelined kernel (two track slots per persistent CTA): same arithmetic as the
-    production kernel, different partial-sum order; checked like it (first-iteration J^T r, oracle spread)."""
-    monkeypatch.setenv("ICT_PIPE", "1")
-    case = make_case(seed=31, ntracks=33)                      # odd count: one CTA ends with a single busy slot
-    g = gpu_run(ict, case)
-    m, spread = check_against_oracle_spread(g, case, orc)
-    assert m["frac_same"] >= 0.93 and m["worst_rot"] <= 1e-5, m
-    case = make_case(seed=21, w=1920, h=1080, psz=32, npts=4, ntracks=300)
-    g = gpu_run(ict, case, trace_cap=48)
-    check_against_oracle_spread(g, case, orc, trace_cap=48)
-    monkeypatch.delenv("ICT_PIPE")
-    g0 = gpu_run(ict, case, trace_cap=48)
-    assert np.array_equal(g["pt2d"], g0["pt2d"])
-    assert np.array_equal(g["trace"][:, 0, 15], g0["trace"][:, 0, 15])
-
-
 # psz 32 has its own kernels (K2v2 for the default order, K2x for the reference order): their edge cases
 CASES32 = [
     dict(seed=61, npts=1),                                   # one point: rank(H) <= 2, Eigen's truncated solve
@@ -331,6 +310,28 @@ def test_psz32_kernels_edge_cases(ict, orc, kw):
     gn = gpu_run(ict, case, trace_cap=0)                     # the production instantiation (no trace records)
     assert np.array_equal(gn["p_out"], g["p_out"]) and np.array_equal(gn["iters"], g["iters"])
     assert np.array_equal(gn["npixres"], g["npixres"])
+
+
+@pytest.mark.parametrize("npts", [1, 2, 4, 5, 8])
+def test_k2r_equals_k2x(ict, npts):
+    """The two reference-order kernels for 32x32 patches — K2r (steepest-descent images resident in shared memory, 2-D
+    TMA windows; the default route) and K2x (producer/chain ring; tracker knob "no_k2r") — agree bit for bit: every
+    iteration's J^T r and delta_p, iteration counts, pixel-residual counts, poses.  1..4 points run K2r with four
+    producer warps, 5..8 with eight."""
+    case = make_case(psz=32, w=1280, h=704, seed=160 + npts, npts=npts, ntracks=24, scale=1.5)
+    c = case
+    op = ict.OptParam.from_buffer_copy(bytes(c["op"]))
+    fr = ict.Frames(2, c["w"], c["h"], c["lv_f"], c["psz"])
+    fr.upload(0, np.stack([c["A"], c["B"]]))
+    tr = ict.Tracker(op, c["sc"].fc, c["sc"].cc, c["sc"].wh)          # reference order is the library default
+    tr.set_points(c["pt_off"], c["pts"].copy())
+    r = tr.track_batch(fr, 0, 1, np.zeros((c["T"], 6)), trace_cap=48)
+    tr.set_knob("no_k2r", 1)
+    x = tr.track_batch(fr, 0, 1, np.zeros((c["T"], 6)), trace_cap=48)
+    assert np.array_equal(r["trace"][..., :16], x["trace"][..., :16])
+    assert np.array_equal(r["p_out"], x["p_out"]) and np.array_equal(r["iters"], x["iters"])
+    assert np.array_equal(r["npixres"], x["npixres"])
+    tr.close(); fr.close()
 
 
 def test_psz32_kernels_points_out_of_view(ict, orc):
@@ -498,6 +499,30 @@ def test_stream_entry_points_equal_blocking_ones(ict):
         st.synchronize()
         assert np.array_equal(h_pout.numpy(), ref["p_out"]), step
         assert np.array_equal(h_iters.numpy(), ref["iters"]) and np.array_equal(h_npix.numpy(), ref["npixres"])
+    # ict_track_batch_stream after a BLOCKING ict_tracker_set_points and after ict_tracker_set_points_dev: the points'
+    # copy lane was never started by those calls, the stream call has to cope (round-1 advisor finding)
+    tb = ict.Tracker(op, case["sc"].fc, case["sc"].cc, case["sc"].wh)
+    tb.set_points(case["pt_off"], case["pts"].copy())
+    h_ref0 = torch.zeros(T, dtype=torch.int32).pin_memory()
+    for variant in ("blocking", "dev"):
+        if variant == "dev":
+            d_off = torch.from_numpy(case["pt_off"]).cuda()
+            d_pts = torch.from_numpy(case["pts"].copy()).cuda()
+            tb.set_points_dev(T, d_off.data_ptr(), d_pts.data_ptr(), T * P, P)
+            torch.cuda.synchronize()
+        h_pout.zero_()
+        rc = lib.ict_track_batch_stream(tb.h_, fr.h_, v(h_ref0.data_ptr()), v(h_new.data_ptr()), v(h_pin.data_ptr()),
+                                        v(h_pout.data_ptr()), v(h_iters.data_ptr()), v(h_npix.data_ptr()), v(st.cuda_stream))
+        assert rc == 0, (variant, lib.ict_last_error())
+        st.synchronize()
+        assert np.array_equal(h_pout.numpy(), ref["p_out"]), variant
+        assert np.array_equal(h_iters.numpy(), ref["iters"]), variant
+    # a frame index beyond the store is refused before anything is enqueued
+    h_bad = torch.full((T,), 7, dtype=torch.int32).pin_memory()
+    rc = lib.ict_track_batch_stream(tb.h_, fr.h_, v(h_ref0.data_ptr()), v(h_bad.data_ptr()), v(h_pin.data_ptr()),
+                                    v(h_pout.data_ptr()), v(h_iters.data_ptr()), v(h_npix.data_ptr()), v(st.cuda_stream))
+    assert rc == 2
+    tb.close()
     for t_ in trk:
         t_.close()
     fr.close()
