@@ -129,6 +129,14 @@ int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
  *   "seq_launches" 1: ict_track_sequence issues one launch per frame step even where one kernel could loop over the chain */
 int ict_tracker_set_knob(ict_tracker* tr, const char* name, int value);
 
+/* Teacher forcing for parity tests of the fast mode (sum order 0; the reference-order kernels ignore it): poses is a host
+ * array float[T * trace_cap * 8]; in the next ict_track_batch call WITH a trace of the same trace_cap, after the
+ * iteration that fills trace record r of track t the pose coefficients become poses[(t*trace_cap + r)*8 + 0..5] (e.g. the
+ * oracle's) instead of the kernel's own p + delta_p, and the level continues iff [.. + 6] != 0.  The trace then holds the
+ * kernel's own J^T r and delta_p evaluated at the teacher's poses: identical inputs at EVERY iteration
+ * (odometer.cpp:344-419).  poses == NULL clears it. */
+int ict_tracker_set_teacher(ict_tracker* tr, const float* poses, int trace_cap);
+
 /* Per-iteration trace record, ICT_TRACE_FLOATS floats:
  *   [0] level  [1] iteration  [2..7] sumsd = J^T r  [8..13] delta_p  [14] normdp  [15] #points visible in new frame
  *   [16..21] sum_k |sd_k * pdiff| — filled by the CPU oracle only (the scale fp32 summation noise is relative to;

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ict_tracker_set_optparam": (C.c_int, [C.c_void_p, C.POINTER(OptParam)]),
     "ict_tracker_set_sum_order": (C.c_int, [C.c_void_p, C.c_int]),
     "ict_tracker_set_knob": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "ict_tracker_set_teacher": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ict_tracker_set_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "ict_tracker_set_points_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_void_p]),
@@ -235,6 +236,15 @@ class Tracker:
     def set_sum_order(self, mode):
         """1 (library default): Eigen packet order, bit-identical to the oracle; 0: fast mode (fixed-order tree sums)."""
         _check(lib().ict_tracker_set_sum_order(self.h_, int(mode)))
+
+    def set_teacher(self, poses):
+        """poses: float32 [T, trace_cap, 8] (pose after each trace record + continue flag) or None; see ictrack.h."""
+        if poses is None:
+            _check(lib().ict_tracker_set_teacher(self.h_, None, 0))
+            return
+        poses = np.ascontiguousarray(poses, np.float32)
+        assert poses.ndim == 3 and poses.shape[0] == self.T and poses.shape[2] == 8
+        _check(lib().ict_tracker_set_teacher(self.h_, _p(poses), poses.shape[1]))
 
     def set_knob(self, name, value):
         """Explicit A/B switches: "no_k2r", "seq_launches" (ictrack.h)."""

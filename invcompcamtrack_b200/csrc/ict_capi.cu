@@ -465,7 +465,8 @@ struct ict_tracker {
   int knob_no_k2r = 0, knob_seq_launches = 0;   // ict_tracker_set_knob
   int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
   const int *big_rf = nullptr, *big_nf = nullptr;   // set by ict_track_batch around run_tracks: per-track frames (host) of the multi-CTA path
-  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big;
+  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, teacher;
+  int teacher_cap = 0;           // ict_tracker_set_teacher: records per track of the staged teacher poses (0: none)
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
 };
@@ -493,7 +494,7 @@ ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const
 void ict_tracker_destroy(ict_tracker* tr) {
   if (!tr) return;
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
-                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big};
+                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->teacher};
   for (DevBuf* x : b) x->release();
   tr->lane.release();
   tr->lane_in.release();
@@ -509,6 +510,20 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op) {
   tr->op.pszd2 = op->psz / 2;                      // the derived fields follow psz (run_io_reprojection_test.cpp:115-117)
   tr->op.pszd2m3 = op->psz + op->psz / 2 - 1;
   tr->op.novals = op->psz * op->psz;
+  return ICT_OK;
+}
+
+int ict_tracker_set_teacher(ict_tracker* tr, const float* poses, int trace_cap) {
+  if (!tr) return fail(ICT_ERR_BAD_ARG, "null argument");
+  if (!poses || trace_cap <= 0) {
+    tr->teacher_cap = 0;
+    return ICT_OK;
+  }
+  if (tr->T <= 0) return fail(ICT_ERR_BAD_ARG, "no points set");
+  const size_t bytes = sizeof(float) * 8 * (size_t)tr->T * trace_cap;
+  CU(tr->teacher.reserve(bytes));
+  CU(cudaMemcpy(tr->teacher.p, poses, bytes, cudaMemcpyHostToDevice));
+  tr->teacher_cap = trace_cap;
   return ICT_OK;
 }
 
@@ -631,6 +646,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.iters = iters_dev;
   prm.trace = trace_dev;
   prm.trace_cap = trace_cap;
+  prm.teacher = (trace_dev && tr->teacher_cap > 0 && tr->teacher_cap == trace_cap) ? tr->teacher.as<float>() : nullptr;
   prm.npixres = npix_dev;
   prm.pt2d_out = tr->pt2d.as<float>();
   prm.T = tr->T;

@@ -335,6 +335,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         // 9b. delta_p = M * J^T r (Eigen's solve tabulated once per level), 10. p += delta_p, G = exp(p)
         const float dpk = fmaf(h1.y, b5, fmaf(h1.x, b4, fmaf(h0.w, b3, fmaf(h0.z, b2, fmaf(h0.y, b1, h0.x * b0)))));
         pk = pk + dpk;
+        const float* tf = nullptr;     // teacher forcing (tests): continue from the oracle's pose, not from this one
+        if (TRACE) {
+          if (prm.teacher && trace && trace_n < prm.trace_cap) {
+            tf = prm.teacher + ((int64_t)t * prm.trace_cap + trace_n) * 8;
+            pk = (lane & 7) < 6 ? tf[lane & 7] : 0.0f;
+          }
+        }
         const float q0 = __shfl_sync(FULL, pk, 0), q1 = __shfl_sync(FULL, pk, 1), q2 = __shfl_sync(FULL, pk, 2);
         const float q3 = __shfl_sync(FULL, pk, 3), q4 = __shfl_sync(FULL, pk, 4), q5 = __shfl_sync(FULL, pk, 5);
         float normdp = fabsf(dpk);                      // lpNorm<1> in the reference's association order
@@ -346,7 +353,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         Gr[3] = Gr[7] = Gr[11] = 0.0f;
         se3_exp_regs(Gr, q0, q1, q2, q3, q4, q5, S.G, S.p);
         if (it == 0) normdp_init = normdp;
-        const int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
+        int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
+        if (TRACE) {
+          if (tf) cont = tf[6] != 0.0f;
+        }
         if (lane == 0) {
           *reinterpret_cast<float4*>(S.G) = make_float4(Gr[0], Gr[1], Gr[2], Gr[3]);
           *reinterpret_cast<float4*>(S.G + 4) = make_float4(Gr[4], Gr[5], Gr[6], Gr[7]);

@@ -39,6 +39,10 @@ struct TrackParams {
   int* iters;                      // [T*L] or null
   float* trace;                    // [T*trace_cap*16] or null
   int trace_cap;
+  const float* teacher;            // [T*trace_cap*8] or null (tests): teacher forcing for the fast-mode kernels — after
+                                   //    iteration record r of track t the pose coefficients become teacher[(t*cap+r)*8 + 0..5]
+                                   //    instead of the kernel's own p + delta_p, and the loop continues iff [6] != 0; the
+                                   //    trace still records the kernel's OWN J^T r and delta_p.  Needs trace != null.
   long long* npixres;              // [T] or null
   float* pt2d_out;                 // [2*total] or null: reference 2-D points at lv_l (Get2DPoints)
   int T;                           // tracks in this launch

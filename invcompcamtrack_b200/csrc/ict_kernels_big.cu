@@ -406,18 +406,18 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
 }
 
 // ---- reference-order (sum_mode 1) variants: one CTA, one thread per (quantity, chain) ---------------------------
-__device__ __forceinline__ float big_sd_at(const BigArgs& a, int q, long long e) {
-  const long long i = e / a.prm.op.novals;
+// sd_q of element e with the reference's roundings (odometer.cpp:317-326): sd1 = gx*c0, sd2 = gy*c1, the others
+// fl(fl(gx*ca) + fl(gy*cb)).  Branch-free (the chains of different quantities share a warp: a switch here made every
+// lane wait for its loads inside its own branch, one branch after the other, ~2500 cycles per element) so that the
+// loads of many elements can be in flight together (eigen_chain_prefetch).
+__device__ __forceinline__ float big_sd_at(const BigArgs& a, int q, int e) {
+  const int n = a.prm.op.novals;
+  const int i = n == 1 ? e : e / n;
   const float gx = a.w.gx[e], gy = a.w.gy[e];
   const float* cf = a.w.coef;
-  switch (q) {
-    case 0: return gx * cf[0 * (long long)a.P + i];
-    case 1: return gy * cf[1 * (long long)a.P + i];
-    case 2: return gx * cf[2 * (long long)a.P + i] + gy * cf[3 * (long long)a.P + i];
-    case 3: return gx * cf[4 * (long long)a.P + i] + gy * cf[5 * (long long)a.P + i];
-    case 4: return gx * cf[6 * (long long)a.P + i] + gy * cf[7 * (long long)a.P + i];
-    default: return gx * cf[8 * (long long)a.P + i] + gy * cf[9 * (long long)a.P + i];
-  }
+  const int ja = q < 2 ? q : 2 * q - 2, jb = q < 2 ? q : 2 * q - 1;
+  const float tx = gx * cf[ja * (long long)a.P + i], ty = gy * cf[jb * (long long)a.P + i];
+  return q == 0 ? tx : (q == 1 ? ty : tx + ty);
 }
 
 __global__ void __launch_bounds__(192) k_big_level_hessian_exact(const BigArgs a) {
@@ -613,7 +613,10 @@ __device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, floa
     for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
     lu6_solve_exact(L->lu, sumsd, dp);   // == lu6_solve, straight-line
     float pnew[6];
-    for (int k = 0; k < 6; ++k) { pnew[k] = L->p[k] + dp[k]; S->p[k] = pnew[k]; }
+    const float* tf = nullptr;       // teacher forcing (tests): continue from the oracle's pose
+    if (a.prm.teacher && a.prm.trace && L->trace_n < a.prm.trace_cap)
+      tf = a.prm.teacher + ((int64_t)a.t * a.prm.trace_cap + L->trace_n) * 8;
+    for (int k = 0; k < 6; ++k) { pnew[k] = tf ? tf[k] : L->p[k] + dp[k]; S->p[k] = pnew[k]; }
     se3_exp<float>(S->G, pnew);
     const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
     const int it = L->it;
@@ -635,7 +638,7 @@ __device__ __forceinline__ void dense_iter_finish(const BigArgs& a, int sl, floa
     S->npix = L->npix + (long long)nvis * op.novals;
     S->it = it + 1;
     if (a.prm.iters) a.prm.iters[(int64_t)a.t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = it + 1;
-    S->cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);
+    S->cont = tf ? (tf[6] != 0.0f) : ((it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio));
     S->ticket = 0;
   }
 }

@@ -41,7 +41,7 @@ def oracle_run(orc, case, trace_cap=64, sum_mode=0, nthreads=0, p_in=None):
     return out
 
 
-def gpu_run(ict, case, trace_cap=64, p_in=None, sum_order=0):
+def gpu_run(ict, case, trace_cap=64, p_in=None, sum_order=0, teacher=None):
     """sum_order 0 = the opt-in fast mode (tree sums), 1 = the library default (reference order), None = leave the
     library default untouched."""
     c = case
@@ -53,6 +53,8 @@ def gpu_run(ict, case, trace_cap=64, p_in=None, sum_order=0):
         tr.set_sum_order(sum_order)
     pts = c["pts"].copy()
     tr.set_points(c["pt_off"], pts)
+    if teacher is not None:
+        tr.set_teacher(teacher)
     T = c["T"]
     p_in = np.zeros((T, 6)) if p_in is None else p_in
     out = tr.track_batch(fr, 0, 1, p_in, trace_cap=trace_cap)
@@ -84,7 +86,8 @@ def check_parity(g, o, case, jtr_tol=1e-5, rot_tol=1e-5, trans_tol=1e-5, min_sam
         Later iterations are compared too but against jtr_traj_tol: from the second iteration on the two sides
         evaluate J^T r at poses that already differ in the last fp32 bits, and d(J^T r) = H * d(pose) amplifies
         that (the oracle's own summation orders differ from each other by ~3e-4 there, tests/test_oracle_golden.py).
-        tests/test_gpu_parity.py::test_jtr_teacher_forced checks every iteration on identical inputs instead.
+        tests/test_gpu_parity.py::test_jtr_teacher_forced checks every iteration on identical inputs instead (the
+        fast-mode kernels are fed the oracle's pose after each iteration: teacher_from_oracle below).
       * identical iteration counts on >= 99 % of (track, level);
       * converged rotation within 1e-5 rad (all tracks with identical counts);
       * translation within 1e-5 relative on >= 99 % of those tracks and within 10x that on all of them.
@@ -150,3 +153,44 @@ def check_against_oracle_spread(g, case, orc, trace_cap=64, slack=2.0):
     assert m["median_tr"] <= slack * max(s["median_tr"] for s in spread) + 1e-6, (m, spread)
     assert m["worst_rot"] <= slack * max(s["worst_rot"] for s in spread) + 1e-6, (m, spread)
     return m, spread
+
+
+def teacher_from_oracle(o, p_in, trace_cap):
+    """Teacher-forcing input for ict_tracker_set_teacher from an oracle run with a trace (donorm == 0): the oracle's
+    fp32 pose coefficients after every iteration — cpos_p += delta_p in fp32, pose.cpp:116-129 — and whether its loop
+    went on at the same level."""
+    tr = o["trace"]
+    T = tr.shape[0]
+    te = np.zeros((T, trace_cap, 8), np.float32)
+    for t in range(T):
+        p = np.asarray(p_in[t], np.float64).astype(np.float32)
+        n = int((tr[t, :, 0] >= 0).sum())
+        assert n < trace_cap, "trace_cap too small for teacher forcing"
+        for k in range(n):
+            p = (p + tr[t, k, 8:14].astype(np.float32)).astype(np.float32)
+            te[t, k, :6] = p
+            te[t, k, 6] = 1.0 if (k + 1 < n and tr[t, k + 1, 0] == tr[t, k, 0]) else 0.0
+    return te
+
+
+def teacher_forced_errors(g, o):
+    """Per-iteration agreement of a teacher-forced run g with the oracle o on IDENTICAL inputs at every iteration:
+    worst |J^T r difference| / sum_k|sd_k * pdiff| and worst |delta_p difference|_inf relative to the first step of the
+    level, |delta_p(it = 0)|_inf — the scale the reference's own stop rule measures steps against (normdp / normdp_init,
+    odometer.cpp:344-346); relative to the step itself the figure is meaningless near convergence, where delta_p is the
+    image of fp32 summation noise in J^T r."""
+    worst_jtr, worst_dp, nrec = 0.0, 0.0, 0
+    for t in range(o["trace"].shape[0]):
+        gt_, ot_ = g["trace"][t], o["trace"][t]
+        n = int((ot_[:, 0] >= 0).sum())
+        assert int((gt_[:, 0] >= 0).sum()) == n, "teacher forcing must reproduce the oracle's iteration structure"
+        for k in range(n):
+            assert gt_[k, 0] == ot_[k, 0] and gt_[k, 1] == ot_[k, 1]
+            scale = np.maximum(ot_[k, 16:22].astype(np.float64), 1e-30)
+            worst_jtr = max(worst_jtr, float((np.abs(gt_[k, 2:8].astype(np.float64) - ot_[k, 2:8]) / scale).max()))
+            dpo = ot_[k, 8:14].astype(np.float64)
+            if ot_[k, 1] == 0:
+                dp0 = max(np.abs(dpo).max(), 1e-30)
+            worst_dp = max(worst_dp, float(np.abs(gt_[k, 8:14] - dpo).max() / dp0))
+            nrec += 1
+    return worst_jtr, worst_dp, nrec

@@ -282,6 +282,44 @@ def test_ncc_scoring(ict, orc):
     assert np.abs(got - ref).max() < 2e-5
 
 
+TEACHER = [
+    # dp_tol: delta_p = H^-1 J^T r inherits the J^T r error (~1e-6 of sum|sd*r|, while J^T r itself is a small difference
+    # of large terms) times the conditioning of H, and the fast mode's H comes from tree sums too; measured on B200:
+    # 1.4e-3 / 7.1e-3 / 3.6e-2 / 9.6e-4 of the level's first step.  The oracle's own delta_p moves as much when only
+    # its Eigen packet width changes (tests/test_oracle_golden.py::test_oracle_modes_spread).  Gates = measured x 3.
+    # BASELINE configs[0]/[1] geometry: 8x8 patches, 100 points, 640x480 (K2v8)
+    dict(name="C1", kw=dict(seed=201, w=640, h=480, psz=8, npts=100, ntracks=4), dp_tol=5e-3),
+    # BASELINE configs[2] geometry, well conditioned: 32x32 patches, 16 points per track (K2v2, one CTA of 32 warps)
+    dict(name="C3-16", kw=dict(seed=202, w=1280, h=704, psz=32, npts=16, ntracks=4), dp_tol=2e-2),
+    # ... and the benchmark's own ill-conditioned 4-point tracks
+    dict(name="C3-4", kw=dict(seed=203, w=1280, h=704, psz=32, npts=4, ntracks=16), dp_tol=1e-1),
+    # BASELINE configs[3] geometry: dense, one point per pixel (fused dense kernels), tilted plane
+    dict(name="C4", kw=dict(seed=204, w=320, h=240, lv_f=2, psz=1, dense_border=8, tilt=(0.1, -0.08)), dp_tol=3e-3),
+]
+
+
+@pytest.mark.parametrize("tc", TEACHER, ids=[c["name"] for c in TEACHER])
+def test_jtr_teacher_forced(ict, orc, tc):
+    """north_star's per-iteration gate for the FAST MODE kernels (K2v2, K2v8, fused dense; tree sums, factorised
+    J^T r, per-level solve matrix): the oracle's pose is forced into every iteration (ict_tracker_set_teacher), so both
+    sides evaluate every J^T r and delta_p on identical inputs; J^T r must agree within 1e-5 of sum|sd*r| at EVERY
+    iteration, not only the first (odometer.cpp:344-419); delta_p is gated per case (TEACHER above)."""
+    from helpers import teacher_from_oracle, teacher_forced_errors
+    case = make_case(**tc["kw"])
+    cap = 48
+    o = oracle_run(orc, case, trace_cap=cap)
+    te = teacher_from_oracle(o, np.zeros((case["T"], 6)), cap)
+    g = gpu_run(ict, case, trace_cap=cap, sum_order=0, teacher=te)
+    jtr, dp, nrec = teacher_forced_errors(g, o)
+    assert nrec >= 8 * case["T"]
+    print("teacher-forced %s: %d records, worst J^T r error %.2e of sum|sd*r|, worst delta_p error %.2e of the level's first step"
+          % (tc["name"], nrec, jtr, dp))
+    assert jtr <= 1e-5, (tc["name"], jtr, dp)
+    assert dp <= tc["dp_tol"], (tc["name"], jtr, dp)
+    # forced all the way: the final pose is the oracle's last forced pose, the iteration counts are the oracle's
+    assert np.array_equal(g["iters"], o["iters"])
+
+
 # psz 32 has its own kernels (K2v2 for the default order, K2x for the reference order): their edge cases
 CASES32 = [
     dict(seed=61, npts=1),                                   # one point: rank(H) <= 2, Eigen's truncated solve
