@@ -756,26 +756,6 @@ __device__ __forceinline__ float eigen_chain(F v, int c, int as2, int valid) {
   for (int e = c + 8; e < lim; e += 8) s = s + v(e);
   return s;
 }
-// The same chain with the operands of thirty-two consecutive additions fetched before the first of them is performed:
-// same additions, same order, same bits — but the (global-memory) loads behind v() overlap instead of each waiting for
-// the previous addition.  For chains over arrays in global memory (multi-CTA path: one thread per chain over up to
-// millions of elements, where the dependent-load form ran at ~1.6 us per element).
-template <typename F>
-__device__ __forceinline__ float eigen_chain_prefetch(F v, int c, int as2, int valid) {
-  if (c >= as2) return 0.0f;
-  float s = c < valid ? v(c) : 0.0f;
-  const int lim = as2 < valid ? as2 : valid;
-  int e = c + 8;
-  for (; e + 8 * 31 < lim; e += 8 * 32) {
-    float t[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = v(e + 8 * j);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s = s + t[j];
-  }
-  for (; e < lim; e += 8) s = s + v(e);
-  return s;
-}
 // combine the eight chains + the odd packet + the scalar tail exactly like redux_impl::run
 template <typename F>
 __device__ __forceinline__ float eigen_finish(const float* ch, F v, int N, int valid) {

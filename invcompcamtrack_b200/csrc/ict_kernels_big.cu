@@ -34,10 +34,20 @@ struct BigWork {
   float *coef, *w, *mean, *Xc, *Yc, *Zc;
   int *base, *vis;
   float* part;      // [ncta][21]
+  float* prod;      // reference-order sums: six product arrays, chain-major — prod[(q*8 + c)*cstride + j] = value of
+                    // quantity q at element e = 8 j + c (the elements of Eigen's chain c, contiguous)
+  long long cstride;   // floats per chain row of prod (a multiple of BIG_CHUNK)
   int ncta;
 };
 
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+#define BIG_CHUNK 512          /* chain elements per staged chunk (2 KB) of the reference-order chain kernel */
+#define BIG_STAGES 4
+static long long big_cstride(int64_t Nfull) {
+  const long long nj = (Nfull + 7) / 8;
+  return ((nj + BIG_CHUNK - 1) / BIG_CHUNK) * BIG_CHUNK;
+}
 
 static int big_ncta(int64_t E) {
   // at most four 256-thread CTAs per SM (the streaming kernels use up to 64 registers): one resident wave, no tail.
@@ -56,6 +66,7 @@ size_t bigtrack_work_bytes(const ict_optparam& op, int64_t npts) {
   b += al(sizeof(float) * 10 * P) + al(sizeof(float) * 4 * P) + 4 * al(sizeof(float) * P);
   b += 2 * al(sizeof(int) * P);
   b += al(sizeof(float) * 21 * big_ncta(E));
+  b += al(sizeof(float) * 48 * (size_t)big_cstride((int64_t)op.maxpttrack * op.novals));
   return b;
 }
 
@@ -77,7 +88,9 @@ static BigWork carve(const ict_optparam& op, int64_t npts, void* work) {
   w.Zc = (float*)c; c += al(sizeof(float) * P);
   w.base = (int*)c; c += al(sizeof(int) * P);
   w.vis = (int*)c; c += al(sizeof(int) * P);
-  w.part = (float*)c;
+  w.part = (float*)c; c += al(sizeof(float) * 21 * big_ncta(E));
+  w.prod = (float*)c;
+  w.cstride = big_cstride((int64_t)op.maxpttrack * op.novals);
   w.ncta = big_ncta(E);
   return w;
 }
@@ -373,7 +386,7 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
   BigState* S = a.w.st;
   if (!S->cont) return;
   __shared__ float s_sum[21];
-  if (ncta == 1) {   // reference-order sums were completed by k_big_iter_sums_exact: take them as they are
+  if (ncta == 1) {   // reference-order sums were completed by k_big_chains: take them as they are
     if (threadIdx.x < 6) s_sum[threadIdx.x] = a.w.part[threadIdx.x];
     __syncthreads();
   } else {
@@ -405,44 +418,134 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
   }
 }
 
-// ---- reference-order (sum_mode 1) variants: one CTA, one thread per (quantity, chain) ---------------------------
-// sd_q of element e with the reference's roundings (odometer.cpp:317-326): sd1 = gx*c0, sd2 = gy*c1, the others
-// fl(fl(gx*ca) + fl(gy*cb)).  Branch-free (the chains of different quantities share a warp: a switch here made every
-// lane wait for its loads inside its own branch, one branch after the other, ~2500 cycles per element) so that the
-// loads of many elements can be in flight together (eigen_chain_prefetch).
-__device__ __forceinline__ float big_sd_at(const BigArgs& a, int q, int e) {
+// ---- reference-order (sum_mode 1) variants -----------------------------------------------------------------------------
+// ---- reference-order sums over arrays too long for one thread per chain -----------------------------------------------
+// Eigen's chain c of a sum adds the elements c, c+8, c+16, ... one after the other: 4 cycles per addition whatever
+// else happens, so a sum over E elements costs E/2 cycles at best (1 M cycles = 0.5 ms for a 1080p dense template).
+// The first form of this path ran each chain as one thread fetching its operands from five global arrays as it went
+// (~2500 cycles per element: 12.5 s per dense TrackPose).  Now in two phases:
+//   1. k_big_products (all SMs, streaming): the values to be summed — sd_k * pdiff for the six J^T r sums, sd_a * sd_b
+//      for six of the 21 Hessian sums per pass — with the reference's roundings, written CHAIN-MAJOR (the elements of
+//      chain c of quantity q contiguous), so that
+//   2. k_big_chains (one warp per quantity, lane c = chain c) streams its eight rows through a four-stage
+//      shared-memory ring with bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts, 2 KB per chain
+//      and stage) and does nothing but LDS.128 + four dependent additions per four elements.
+// Same additions in the same order as eigen_chain: the sums are bit-identical to the one-thread form (tested against
+// the oracle on dense alignment and on tracks of 700-900 8x8 patches).
+template <int MODE>   // 0: iteration (sd_q * pnew); 1: Hessian, pairs 6*pass .. 6*pass+5 of ComputeHessian's order
+__global__ void __launch_bounds__(256) k_big_products(const BigArgs a, int pass) {
+  if (MODE == 0 && !a.w.st->cont) return;
   const int n = a.prm.op.novals;
-  const int i = n == 1 ? e : e / n;
-  const float gx = a.w.gx[e], gy = a.w.gy[e];
+  const long long lim = a.E;                       // elements beyond E are zeros the reference adds nothing for
+  const long long nj = (lim + 7) / 8;
   const float* cf = a.w.coef;
-  const int ja = q < 2 ? q : 2 * q - 2, jb = q < 2 ? q : 2 * q - 1;
-  const float tx = gx * cf[ja * (long long)a.P + i], ty = gy * cf[jb * (long long)a.P + i];
-  return q == 0 ? tx : (q == 1 ? ty : tx + ty);
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < nj; j += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const long long e = 8 * j + c;
+      float v[6];
+      if (e < lim) {
+        const long long i = n == 1 ? e : e / n;
+        const float gx = a.w.gx[e], gy = a.w.gy[e];
+        float sd[6];
+        sd[0] = gx * cf[0 * (long long)a.P + i];
+        sd[1] = gy * cf[1 * (long long)a.P + i];
+        sd[2] = gx * cf[2 * (long long)a.P + i] + gy * cf[3 * (long long)a.P + i];
+        sd[3] = gx * cf[4 * (long long)a.P + i] + gy * cf[5 * (long long)a.P + i];
+        sd[4] = gx * cf[6 * (long long)a.P + i] + gy * cf[7 * (long long)a.P + i];
+        sd[5] = gx * cf[8 * (long long)a.P + i] + gy * cf[9 * (long long)a.P + i];
+        if (MODE == 0) {
+          const float pd = a.w.pnew[e];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) v[q] = sd[q] * pd;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const int idx = 6 * pass + q;      // pair (x, y), x <= y, in row-major upper-triangle order
+            int x = 0, y = 0, k = 0;
+#pragma unroll
+            for (int aa = 0; aa < 6; ++aa)
+#pragma unroll
+              for (int bb = aa; bb < 6; ++bb) { if (k == idx) { x = aa; y = bb; } ++k; }
+            float sx = sd[0], sy = sd[0];
+#pragma unroll
+            for (int m = 1; m < 6; ++m) { sx = x == m ? sd[m] : sx; sy = y == m ? sd[m] : sy; }
+            v[q] = idx < 21 ? sx * sy : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a.w.prod[(q * 8 + c) * a.w.cstride + j] = v[q];
+      }
+    }
+  }
 }
 
-__global__ void __launch_bounds__(192) k_big_level_hessian_exact(const BigArgs a) {
-  __shared__ float s_chain[21 * 8];
+// One CTA (one warp) per quantity q < nq.  out[q] = the Eigen-order sum of the quantity's E values (zeros up to
+// Nfull), finished like redux_impl::run with the few tail elements re-read from the product rows.
+__global__ void __launch_bounds__(32) k_big_chains(const BigArgs a, int nq, float* out, int iteration) {
+  if (iteration && !a.w.st->cont) return;
+  extern __shared__ __align__(128) float s_ring[];     // [BIG_STAGES][8][BIG_CHUNK]
+  __shared__ unsigned long long s_full[BIG_STAGES];
+  __shared__ float s_ch[8];
+  const int q = blockIdx.x, lane = threadIdx.x;
+  if (q >= nq) return;
+  const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E;
+  const int as2 = (Nfull / 8) * 8, lim = as2 < E ? as2 : E;
+  const float* rows = a.w.prod + (long long)q * 8 * a.w.cstride;
+  // chain c has cnt_c = #{e < lim : e % 8 == c} elements; all chains need ceil(lim / 8) positions at most
+  const int njmax = (lim + 7) / 8;
+  const int nchunk = (njmax + BIG_CHUNK - 1) / BIG_CHUNK;
+  if (lane < BIG_STAGES) mbar_init(&s_full[lane], 1);
+  mbar_fence_init();
+  __syncwarp();
+  auto issue = [&](int chunk) {     // lane 0: the eight rows' chunk into stage chunk % BIG_STAGES
+    const int st = chunk % BIG_STAGES;
+    mbar_expect_tx(&s_full[st], 8u * BIG_CHUNK * sizeof(float));
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      bulk_g2s(s_ring + (st * 8 + c) * BIG_CHUNK, rows + c * a.w.cstride + (long long)chunk * BIG_CHUNK, BIG_CHUNK * sizeof(float),
+               &s_full[st]);
+  };
+  if (lane == 0)
+    for (int k = 0; k < BIG_STAGES && k < nchunk; ++k) issue(k);
+  const int c = lane & 7;
+  const int cnt = c < lim ? (lim - c + 7) / 8 : 0;      // this chain's elements
+  float acc = -0.0f;                                     // -0 + x == x: the chain starts with its first element
+  for (int chunk = 0; chunk < nchunk; ++chunk) {
+    const int st = chunk % BIG_STAGES;
+    mbar_wait(&s_full[st], (chunk / BIG_STAGES) & 1);
+    if (lane < 8) {
+      const float4* p4 = reinterpret_cast<const float4*>(s_ring + (st * 8 + c) * BIG_CHUNK);
+      const int have = min(BIG_CHUNK, cnt - chunk * BIG_CHUNK);     // may be <= 0 for the last chunk of a short chain
+      int i = 0;
+      for (; i + 16 <= have; i += 16) {
+        const float4 v0 = p4[i / 4], v1 = p4[i / 4 + 1], v2 = p4[i / 4 + 2], v3 = p4[i / 4 + 3];
+        acc = acc + v0.x; acc = acc + v0.y; acc = acc + v0.z; acc = acc + v0.w;
+        acc = acc + v1.x; acc = acc + v1.y; acc = acc + v1.z; acc = acc + v1.w;
+        acc = acc + v2.x; acc = acc + v2.y; acc = acc + v2.z; acc = acc + v2.w;
+        acc = acc + v3.x; acc = acc + v3.y; acc = acc + v3.z; acc = acc + v3.w;
+      }
+      const float* p1 = reinterpret_cast<const float*>(p4);
+      for (; i < have; ++i) acc = acc + p1[i];
+    }
+    __syncwarp();                                        // every chain lane has read the stage: refill it
+    if (lane == 0 && chunk + BIG_STAGES < nchunk) issue(chunk + BIG_STAGES);
+  }
+  if (lane < 8) s_ch[lane] = cnt > 0 ? acc : 0.0f;
+  __syncwarp();
+  if (lane == 0) {
+    auto val = [&](int e) { return rows[(e & 7) * a.w.cstride + (e >> 3)]; };
+    out[q] = eigen_finish(s_ch, val, Nfull, E);
+  }
+}
+
+// factorisation + state of a level after the 21 reference-order Hessian sums (part[0..20]) are in
+__global__ void __launch_bounds__(32) k_big_hessian_exact_finish(const BigArgs a) {
   __shared__ float s_H[21];
   const int tid = threadIdx.x;
-  const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E, as2 = (Nfull / 8) * 8;
-  auto pair_of = [](int q, int& x, int& y) {
-    int k = 0;
-    for (int aa = 0; aa < 6; ++aa)
-      for (int bb = aa; bb < 6; ++bb) { if (k == q) { x = aa; y = bb; } ++k; }
-  };
-  if (tid < 21 * 8) {
-    int x = 0, y = 0;
-    pair_of(tid >> 3, x, y);
-    s_chain[tid] = eigen_chain_prefetch([&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, tid & 7, as2, E);
-  }
-  __syncthreads();
-  if (tid < 21) {
-    int x = 0, y = 0;
-    pair_of(tid, x, y);
-    s_H[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, x, e) * big_sd_at(a, y, e); }, Nfull, E);
-  }
-  __syncthreads();
-  if (tid < 32) lu6_factor_warp(s_H, a.w.st->lu);
+  if (tid < 21) s_H[tid] = a.w.part[tid];
+  __syncwarp();
+  lu6_factor_warp(s_H, a.w.st->lu);
   if (tid == 0) {
     BigState* S = a.w.st;
     const ict_optparam& op = a.prm.op;
@@ -476,17 +579,6 @@ __global__ void __launch_bounds__(256) k_big_iter_pdiff(const BigArgs a, int sl)
     }
     a.w.pnew[e] = pd;
   }
-}
-
-__global__ void __launch_bounds__(64) k_big_iter_sums_exact(const BigArgs a) {
-  if (!a.w.st->cont) return;
-  __shared__ float s_chain[6 * 8];
-  const int tid = threadIdx.x;
-  const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E, as2 = (Nfull / 8) * 8;
-  if (tid < 48) s_chain[tid] = eigen_chain_prefetch([&](int e) { return big_sd_at(a, tid >> 3, e) * a.w.pnew[e]; }, tid & 7, as2, E);
-  __syncthreads();
-  if (tid < 6)   // the finishing kernel reads partials as part[cta*21 + k] with ncta CTAs: publish as CTA 0 of 1
-    a.w.part[tid] = eigen_finish(s_chain + 8 * tid, [&](int e) { return big_sd_at(a, tid, e) * a.w.pnew[e]; }, Nfull, E);
 }
 
 // ==================================================================================================
@@ -836,6 +928,17 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const bool ex = prm.sum_mode != 0;   // reference-order sums
   const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !ict_knob("ICT_DENSE_V1");
   int nl = 0;
+  const size_t chain_smem = sizeof(float) * BIG_STAGES * 8 * BIG_CHUNK;    // 64 KB
+  if (ex) {
+    static bool attr_dev[64] = {};            // function attributes are per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_dev[dev_ & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(k_big_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
+      if (e != cudaSuccess) return e;
+      attr_dev[dev_ & 63] = true;
+    }
+  }
   k_big_init<<<ncta, 256, 0, st>>>(a, fused ? 1 : 0); ++nl;
   k_big_project_ref<<<pcta, 256, 0, st>>>(a); ++nl;
   for (int sl = op.lv_f; sl >= op.lv_l && fused; --sl) {   // dense path: one launch per level + one per iteration
@@ -880,7 +983,11 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
     k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1, ex ? 1 : 0); ++nl; }
     if (ex) {
-      k_big_level_hessian_exact<<<1, 192, 0, st>>>(a); ++nl;
+      for (int pass = 0; pass < 4; ++pass) {      // 21 sums, six product rows at a time
+        k_big_products<1><<<ncta, 256, 0, st>>>(a, pass); ++nl;
+        k_big_chains<<<pass < 3 ? 6 : 3, 32, chain_smem, st>>>(a, pass < 3 ? 6 : 3, a.w.part + 6 * pass, 0); ++nl;
+      }
+      k_big_hessian_exact_finish<<<1, 32, 0, st>>>(a); ++nl;
     } else {
       k_big_level_hessian<<<ncta, 256, 0, st>>>(a); ++nl;
       k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
@@ -894,7 +1001,8 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
       if (ex) {
         if (pn) k_big_iter_pdiff<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_pdiff<false><<<ncta, 256, 0, st>>>(a, sl);
         ++nl;
-        k_big_iter_sums_exact<<<1, 64, 0, st>>>(a); ++nl;
+        k_big_products<0><<<ncta, 256, 0, st>>>(a, 0); ++nl;
+        k_big_chains<<<6, 32, chain_smem, st>>>(a, 6, a.w.part, 1); ++nl;
       } else {
         if (pn) k_big_iter_elems<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_elems<false><<<ncta, 256, 0, st>>>(a, sl);
         ++nl;
