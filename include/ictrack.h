@@ -127,6 +127,15 @@ int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
  *   "no_k2r"       1: reference-order 32x32 tracks run the producer/chain-ring kernel K2x even where K2r (resident
  *                     steepest-descent images, TMA windows) applies — same bits, for comparisons
  *   "seq_launches" 1: ict_track_sequence issues one launch per frame step even where one kernel could loop over the chain */
+/*   "keep_state"   1: the reference's state between TrackPose calls.  ResetOdometer runs only from the
+ *                     constructor and Set3Dpoints (odometer.cpp:153, 173), so in the chains of
+ *                     run_track_nposes.cpp:232-258 a point that has left the image keeps the template patch and
+ *                     steepest-descent values of the last level — possibly of an earlier frame step — at which it was
+ *                     visible, and they keep feeding the Hessian.  With this knob every ict_track_batch /
+ *                     ict_track_sequence step starts from the arrays the previous call left (until the next
+ *                     ict_tracker_set_points*).  Reference summation order, psz 8, up to 224 points per track (the
+ *                     drivers' configuration); other configurations return ICT_ERR_UNSUPPORTED.  Default 0: every call
+ *                     starts from zeroed arrays. */
 int ict_tracker_set_knob(ict_tracker* tr, const char* name, int value);
 
 /* Teacher forcing for parity tests of the fast mode (sum order 0; the reference-order kernels ignore it): poses is a host
@@ -206,6 +215,15 @@ int ict_track_batch_stream(ict_tracker* tr, const ict_frames* fs, const int* ref
 int ict_track_pair(const ict_optparam* op, const float fc[2], const float cc[2], const int wh[2],
                    const float* imgA, const float* imgB, double* pt3d, int npts,
                    const double p_in[6], double p_out[6], int* iters, float* trace, int trace_cap);
+
+/* ---- a10/a11: util_getPatch / util_getPatch_grad, utilities.h:74-79, utilities.cpp:55-189 -------------------------
+ * npatch bilinear psz x psz patches around mids[2*i + {0,1}] = (x, y) of level `level` of a device-resident frame:
+ * the reference's placement (ceil(x + 1e-5f), origin ceil + psz/2 - padding), weights and association order; with
+ * op->dopatchnorm the mean (Eigen's packet sum) is subtracted from the INTENSITY patch only (utilities.cpp:111-112,
+ * 187-188).  out_I / out_dx / out_dy: host float[npatch * psz*psz], any may be NULL (util_getPatch == out_I only).
+ * Centres must lie in [0, swo] x [0, sho] of the level, the range the reference samples (odometer.cpp:273-275). */
+int ict_get_patches(const ict_frames* fs, int frame, int level, const ict_optparam* op, int npatch, const float* mids,
+                    float* out_I, float* out_dx, float* out_dy);
 
 /* ---- f1 (next row): NCC hypothesis scoring, run_track_nposes.cpp:271-355 ------------------------------
  * For every point of every track: mean-subtracted psz x psz patches at pt2d_back/refe/forw in frames

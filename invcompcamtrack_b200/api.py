@@ -78,6 +78,8 @@ SIGNATURES = {
     "ict_tracker_get_2dpoints": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ict_track_pair": (C.c_int, [C.POINTER(OptParam), _f, _f, _i, _f, _f, _d, C.c_int, _d, _d, C.c_void_p,
                                  C.c_void_p, C.c_int]),
+    "ict_get_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(OptParam), C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "ict_ncc_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "ict_launch_count": (C.c_int64, [C.c_int]),
@@ -200,6 +202,16 @@ class Frames:
     def build_dev(self, first, count, dev_ptr, u8=False, stream=0):
         fn = lib().ict_frames_build_dev_u8 if u8 else lib().ict_frames_build_dev
         _check(fn(self.h_, first, count, C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+    def get_patches(self, frame, level, op, mids, grad=True):
+        """util_getPatch (grad=False) / util_getPatch_grad: mids [n, 2] (x, y) -> (I, dx, dy) each [n, psz*psz]."""
+        mids = np.ascontiguousarray(mids, np.float32).reshape(-1, 2)
+        n, nv = mids.shape[0], op.psz * op.psz
+        I = np.zeros((n, nv), np.float32)
+        dx = np.zeros((n, nv), np.float32) if grad else None
+        dy = np.zeros((n, nv), np.float32) if grad else None
+        _check(lib().ict_get_patches(self.h_, frame, level, C.byref(op), n, _p(mids), _p(I), _p(dx), _p(dy)))
+        return (I, dx, dy) if grad else I
 
     def download(self, frame):
         I = np.empty(self.plane_floats, np.float32); dx = np.empty_like(I); dy = np.empty_like(I)

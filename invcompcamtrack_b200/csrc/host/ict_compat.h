@@ -9,6 +9,20 @@
 #include <Eigen/Core>
 #else
 namespace Eigen {
+enum { Aligned = 1, Dynamic = -1, RowMajor = 1 };
+// the reference's patch buffers are Eigen::Map<MatrixXfTr, Eigen::Aligned> over caller-owned floats (odometer.h:70-99):
+// only data() is needed on this side
+template <typename M, int A = 0>
+struct Map {
+  float* p;
+  int n;
+  Map(float* d, int rows, int cols = 1) : p(d), n(rows * cols) {}
+  float* data() { return p; }
+  const float* data() const { return p; }
+  int size() const { return n; }
+};
+template <typename S, int R, int C, int O = 0>
+struct Matrix {};
 struct Vector3d {
   double v[3];
   Vector3d() : v{0, 0, 0} {}

@@ -13,6 +13,9 @@ OdometerClass::OdometerClass(PoseClass* pose_in, const optparam* op_in)
   const CamClass* cam = pose->camobj;
   tracker = ict_tracker_create(op, cam->fc(), cam->cc(), cam->wh());
   if (!tracker) report("OdometerClass");
+  // like the reference object, keep the patch / steepest-descent arrays between TrackPose calls (they are reset by
+  // Set3Dpoints only, odometer.cpp:153, 173); configurations the library cannot do that for fall back in TrackPose
+  if (tracker) ict_tracker_set_knob(tracker, "keep_state", 1);
   view = ict_frames_create_view(2, cam->wh()[0], cam->wh()[1], op->lv_f, cam->getpadding());
   if (!view) report("OdometerClass");
   pt2d_lvl.assign(2 * (size_t)op->maxpttrack, 0.0f);
@@ -94,7 +97,12 @@ void OdometerClass::TrackPose(double* p_out) {
   if (!tracker || !view) return;
   if (ict_tracker_set_optparam(tracker, op) != ICT_OK) report("optparam");
   const int rf = 0, nf = 1;
-  if (ict_track_batch(tracker, view, &rf, &nf, p_cur, p_out, iters, nullptr, 0, nullptr) != ICT_OK) {
+  int rc = ict_track_batch(tracker, view, &rf, &nf, p_cur, p_out, iters, nullptr, 0, nullptr);
+  if (rc == ICT_ERR_UNSUPPORTED) {   // no carried state for this configuration: every TrackPose starts from zeroed arrays
+    ict_tracker_set_knob(tracker, "keep_state", 0);
+    rc = ict_track_batch(tracker, view, &rf, &nf, p_cur, p_out, iters, nullptr, 0, nullptr);
+  }
+  if (rc != ICT_OK) {
     report("TrackPose");
     return;
   }

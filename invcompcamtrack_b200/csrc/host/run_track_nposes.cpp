@@ -96,12 +96,24 @@ static int run_batch(const Input& in, const optparam& op, ict_frames* fs, int s0
   ict_tracker* tr = ict_tracker_create(&op, in.fc, in.cc, in.wh);
   if (!tr) { std::printf("ict_tracker_create: %s\n", ict_last_error()); return 1; }
   if (const char* so = std::getenv("ICT_SUM_ORDER")) CHECK(ict_tracker_set_sum_order(tr, std::atoi(so)));
+  // The reference resets its patch / steepest-descent arrays only in Set3Dpoints (odometer.cpp:173): a point that leaves
+  // the image keeps its last template through the rest of the sample's chains.  Reproduced by the tracker's keep_state
+  // (reference order, psz 8, <= 224 points); ICT_KEEP_STATE=0 turns it off (every frame step then starts from zero).
+  int keep = std::getenv("ICT_KEEP_STATE") ? std::atoi(std::getenv("ICT_KEEP_STATE")) : 1;
+  CHECK(ict_tracker_set_knob(tr, "keep_state", keep));
   CHECK(ict_tracker_set_points(tr, T, off.data(), pts.data(), 0));
 
   std::vector<float> q_ref(2 * (size_t)total), q_fwd(2 * (size_t)total), q_back(2 * (size_t)total), corr((size_t)total);
   CHECK(ict_tracker_reproject(tr, p0.data(), q_ref.data()));                                       // :217-225
   std::vector<double> fwd(6 * (size_t)T * (nf + 1)), back(6 * (size_t)T * (nb + 1));
-  CHECK(ict_track_sequence(tr, fs, nb, nf, +1, p0.data(), fwd.data(), nullptr, nullptr));          // :232-239
+  int rc_seq = ict_track_sequence(tr, fs, nb, nf, +1, p0.data(), fwd.data(), nullptr, nullptr);   // :232-239
+  if (rc_seq == ICT_ERR_UNSUPPORTED && keep) {
+    std::printf("note: this configuration runs without the reference's state between frame steps (%s)\n", ict_last_error());
+    keep = 0;
+    CHECK(ict_tracker_set_knob(tr, "keep_state", 0));
+    rc_seq = ict_track_sequence(tr, fs, nb, nf, +1, p0.data(), fwd.data(), nullptr, nullptr);
+  }
+  CHECK(rc_seq);
   CHECK(ict_tracker_reproject(tr, fwd.data() + 6 * (size_t)T * nf, q_fwd.data()));                 // :240-246
   CHECK(ict_track_sequence(tr, fs, nb, nb, -1, p0.data(), back.data(), nullptr, nullptr));         // :250-258
   CHECK(ict_tracker_reproject(tr, back.data() + 6 * (size_t)T * nb, q_back.data()));               // :259-265

@@ -15,7 +15,32 @@ std::map<const float*, DevicePyramid>& registry() {
   static std::map<const float*, DevicePyramid> r;
   return r;
 }
+// every intensity level plane of a host pyramid -> (device store, frame, level), for util_getPatch*
+struct DevicePlane { ict_frames* store; int frame, level; };
+std::map<const float*, DevicePlane>& plane_registry() {
+  static std::map<const float*, DevicePlane> r;
+  return r;
+}
 }  // namespace
+
+void util_getPatch_grad(const float* img, const float* img_dx, const float* img_dy, const float* mid_in,
+                        Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_in_e, Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_dx_in_e,
+                        Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_dy_in_e, const optparam* op, const int width) {
+  (void)img_dx; (void)img_dy; (void)width;     // the device twin carries all three planes and its own row pitch
+  auto it = plane_registry().find(img);
+  if (it == plane_registry().end()) {
+    std::printf("util_getPatch: the plane was not made by util_constructpyramide\n");
+    return;
+  }
+  if (ict_get_patches(it->second.store, it->second.frame, it->second.level, op, 1, mid_in, tmp_in_e->data(),
+                      tmp_dx_in_e ? tmp_dx_in_e->data() : nullptr, tmp_dy_in_e ? tmp_dy_in_e->data() : nullptr) != ICT_OK)
+    std::printf("util_getPatch: %s\n", ict_last_error());
+}
+
+void util_getPatch(const float* img, const float* mid_in, Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_in_e,
+                   const optparam* op, const int width) {
+  util_getPatch_grad(img, nullptr, nullptr, mid_in, tmp_in_e, nullptr, nullptr, op, width);
+}
 
 bool util_find_device_pyramid(const float* level0_plane, ict_frames** store, int* frame) {
   auto it = registry().find(level0_plane);
@@ -28,6 +53,7 @@ bool util_find_device_pyramid(const float* level0_plane, ict_frames** store, int
 void util_release_device_pyramids() {
   for (auto& kv : registry()) ict_frames_destroy(kv.second.store);
   registry().clear();
+  plane_registry().clear();
 }
 
 void util_constructpyramide(const cv::Mat& img, cv::Mat* pyr, cv::Mat* pyr_dx, cv::Mat* pyr_dy, const float** p,
@@ -55,6 +81,7 @@ void util_constructpyramide(const cv::Mat& img, cv::Mat* pyr, cv::Mat* pyr_dx, c
     pyr[l].create(sh[l], sw[l], CV_32F);
     std::memcpy(pyr[l].data, I.data() + off[l], n * sizeof(float));
     p[l] = (const float*)pyr[l].data;
+    plane_registry()[p[l]] = DevicePlane{fs, 0, l};
     if (getgrad) {
       pyr_dx[l].create(sh[l], sw[l], CV_32F);
       pyr_dy[l].create(sh[l], sw[l], CV_32F);

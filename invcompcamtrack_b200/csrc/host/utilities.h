@@ -4,8 +4,10 @@
 //   util_constructpyramide    == utilities.h:63 / utilities.cpp:14-52: builds the pyramid ON THE DEVICE, keeps it there
 //                                and also fills the caller's cv::Mat arrays + pointer tables with host copies
 //   util_SE3_coeff_to_group / util_SE3_group_to_coeff == utilities.h:84-241 (host scalar helpers of PoseClass)
-// util_getPatch / util_getPatch_grad (utilities.h:74-79) have no host twin: patches never leave the device; the NCC
-// scoring that used them in run_track_nposes.cpp:271-355 is ict_ncc_score().
+//   util_getPatch / util_getPatch_grad == utilities.h:74-79 / utilities.cpp:55-189: the plane pointers must be level planes
+//                                made by util_constructpyramide (their device twins are looked up by pointer); one
+//                                GPU round trip per call — the tracker itself never needs them (its patches stay on
+//                                the device; the NCC scoring of run_track_nposes.cpp:271-355 is ict_ncc_score())
 #ifndef ICT_HOST_UTIL_HEADER
 #define ICT_HOST_UTIL_HEADER
 
@@ -26,6 +28,14 @@ typedef ict_optparam optparam;
 void util_constructpyramide(const cv::Mat& img_ao_fmat, cv::Mat* img_ao_fmat_pyr, cv::Mat* img_ao_dx_fmat_pyr,
                             cv::Mat* img_ao_dy_fmat_pyr, const float** img_ao_pyr, const float** img_ao_dx_pyr,
                             const float** img_ao_dy_pyr, const int lv_f, const bool getgrad, const int imgpadding);
+
+typedef Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> MatrixXfTr;   // utilities.h:33
+
+void util_getPatch(const float* img, const float* mid_in, Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_in_e,
+                   const optparam* op, const int width);
+void util_getPatch_grad(const float* img, const float* img_dx, const float* img_dy, const float* mid_in,
+                        Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_in_e, Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_dx_in_e,
+                        Eigen::Map<MatrixXfTr, Eigen::Aligned>* tmp_dy_in_e, const optparam* op, const int width);
 
 // Device twin of a host pyramid made by util_constructpyramide, keyed by the level-0 intensity plane pointer.
 // Returns false for planes this library did not build (OdometerClass then uploads them).

@@ -463,9 +463,11 @@ struct ict_tracker {
   int sum_mode = 1;            // the reference's summation order is the default (ictrack.h, ict_tracker_set_sum_order)
   int force_general = 0;
   int knob_no_k2r = 0, knob_seq_launches = 0;   // ict_tracker_set_knob
+  int keep_state = 0;          // knob "keep_state": template arrays persist between TrackPose calls until the next Set3Dpoints
+  bool state_valid = false;
   int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
   const int *big_rf = nullptr, *big_nf = nullptr;   // set by ict_track_batch around run_tracks: per-track frames (host) of the multi-CTA path
-  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, teacher;
+  DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, teacher, state;
   int teacher_cap = 0;           // ict_tracker_set_teacher: records per track of the staged teacher poses (0: none)
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
@@ -494,7 +496,7 @@ ict_tracker* ict_tracker_create(const ict_optparam* op, const float fc[2], const
 void ict_tracker_destroy(ict_tracker* tr) {
   if (!tr) return;
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
-                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->teacher};
+                 &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->teacher, &tr->state};
   for (DevBuf* x : b) x->release();
   tr->lane.release();
   tr->lane_in.release();
@@ -531,6 +533,7 @@ int ict_tracker_set_knob(ict_tracker* tr, const char* name, int value) {
   if (!tr || !name) return fail(ICT_ERR_BAD_ARG, "null argument");
   if (!strcmp(name, "no_k2r")) tr->knob_no_k2r = value ? 1 : 0;
   else if (!strcmp(name, "seq_launches")) tr->knob_seq_launches = value ? 1 : 0;
+  else if (!strcmp(name, "keep_state")) { tr->keep_state = value ? 1 : 0; tr->state_valid = false; }
   else return fail(ICT_ERR_BAD_ARG, std::string("unknown knob: ") + name);
   return ICT_OK;
 }
@@ -572,6 +575,7 @@ int ict_tracker_set_points(ict_tracker* tr, int T, const int64_t* pt_off, double
   tr->max_pts = max_pts;
   tr->h_off.assign(pt_off, pt_off + T + 1);
   tr->have_2d = false;
+  tr->state_valid = false;     // Set3Dpoints resets the odometer (odometer.cpp:173)
   return ICT_OK;
 }
 
@@ -599,6 +603,7 @@ int ict_tracker_set_points_stream(ict_tracker* tr, int T, const int64_t* pt_off,
   tr->max_pts = max_pts;
   tr->h_off.assign(pt_off, pt_off + T + 1);
   tr->have_2d = false;
+  tr->state_valid = false;     // Set3Dpoints resets the odometer (odometer.cpp:173)
   return ICT_OK;
 }
 
@@ -616,6 +621,7 @@ int ict_tracker_set_points_dev(ict_tracker* tr, int T, const int64_t* pt_off_dev
   tr->max_pts = max_pts;
   tr->h_off.clear();
   tr->have_2d = false;
+  tr->state_valid = false;
   return ICT_OK;
 }
 
@@ -658,6 +664,18 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.seq_step = tr->seq_step;
   prm.knob_no_k2r = tr->knob_no_k2r;
   prm.knob_seq_launches = tr->knob_seq_launches;
+  if (tr->keep_state) {
+    // carried template state: implemented by the reference-order kernel for 8x8 patches (the drivers' configuration)
+    if (!(tr->sum_mode == 1 && !tr->force_general && kx8_supported(tr->op, tr->max_pts)))
+      return fail(ICT_ERR_UNSUPPORTED, "keep_state needs the reference summation order, psz 8 and at most 224 points per track");
+    const int P = tr->max_pts < tr->op.maxpttrack ? tr->max_pts : tr->op.maxpttrack;
+    prm.state_stride = (int64_t)(3 * 64 + 12) * P;
+    const size_t bytes = sizeof(float) * (size_t)prm.state_stride * tr->T;
+    if (tr->state.cap < bytes) tr->state_valid = false;
+    CU(tr->state.reserve(bytes));
+    prm.state = tr->state.as<float>();
+    prm.state_load = tr->state_valid ? 1 : 0;
+  }
   // profiling builds only (ict_knobs.h): these change what the kernels compute or where their serial sections run
   prm.dbg_skip_serial = ict_knob("ICT_DBG_SKIP_SERIAL") ? atoi(ict_knob("ICT_DBG_SKIP_SERIAL")) : 0;
   prm.serial_warp_last = ict_knob("ICT_SERIAL_WARP_LAST") ? 1 : 0;
@@ -681,6 +699,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
     }
   }
   tr->have_2d = true;
+  if (tr->keep_state) tr->state_valid = true;
   return ICT_OK;
 }
 
@@ -858,6 +877,41 @@ int ict_track_pair(const ict_optparam* op, const float fc[2], const float cc[2],
   if (rc == ICT_OK) rc = ict_track_batch(tr, fs, &rf, &nf, p_in, p_out, iters, trace, trace_cap, nullptr);
   ict_tracker_destroy(tr);
   ict_frames_destroy(fs);
+  return rc;
+}
+
+int ict_get_patches(const ict_frames* fs, int frame, int level, const ict_optparam* op, int npatch, const float* mids,
+                    float* out_I, float* out_dx, float* out_dy) {
+  if (!fs || !op || !mids || npatch < 0) return fail(ICT_ERR_BAD_ARG, "ict_get_patches: null argument");
+  if (frames_range_ok(fs, frame, 1)) return ICT_ERR_BAD_ARG;
+  if (fs->view || !fs->I) return fail(ICT_ERR_BAD_ARG, "ict_get_patches: needs a store that owns its pixels (not a view)");
+  if (level < 0 || level > fs->lv_f) return fail(ICT_ERR_BAD_ARG, "ict_get_patches: level out of range");
+  if (op->psz < 1 || op->psz > fs->pad) return fail(ICT_ERR_BAD_ARG, "ict_get_patches: psz must be 1..padding of the store");
+  if (npatch == 0) return ICT_OK;
+  // a centre must keep its (psz+1)^2 footprint inside the padded plane: |x| within the level's extent (odometer.cpp:273-275
+  // tests [0, swo] x [0, sho] before it samples); anything else is refused instead of read out of bounds
+  const float swo = (float)(fs->sw[level] - 2 * fs->pad), sho = (float)(fs->sh[level] - 2 * fs->pad);
+  for (int i = 0; i < npatch; ++i)
+    if (!(mids[2 * i] >= 0 && mids[2 * i + 1] >= 0 && mids[2 * i] <= swo && mids[2 * i + 1] <= sho))
+      return fail(ICT_ERR_BAD_ARG, "ict_get_patches: a centre lies outside [0, swo] x [0, sho] of the level");
+  const size_t n = (size_t)op->psz * op->psz, tot = n * npatch;
+  DevBuf dm, dout;
+  cudaError_t e = dm.reserve(sizeof(float) * 2 * npatch);
+  if (e == cudaSuccess) e = dout.reserve(sizeof(float) * 3 * tot);
+  float* o = dout.as<float>();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dm.p, mids, sizeof(float) * 2 * npatch, cudaMemcpyHostToDevice, 0);
+  const size_t po = (size_t)frame * fs->plane_floats + fs->level_off[level];
+  if (e == cudaSuccess)
+    e = launch_get_patches(fs->I + po, fs->dx + po, fs->dy + po, fs->sw[level], op->psz, op->psz / 2, op->dopatchnorm ? 1 : 0,
+                           npatch, dm.as<float>(), out_I ? o : nullptr, out_dx ? o + tot : nullptr, out_dy ? o + 2 * tot : nullptr, 0);
+  if (e == cudaSuccess && out_I) e = cudaMemcpyAsync(out_I, o, sizeof(float) * tot, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess && out_dx) e = cudaMemcpyAsync(out_dx, o + tot, sizeof(float) * tot, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess && out_dy) e = cudaMemcpyAsync(out_dy, o + 2 * tot, sizeof(float) * tot, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  int rc = ICT_OK;
+  if (e != cudaSuccess) rc = fail(ICT_ERR_CUDA, std::string("ict_get_patches: ") + cudaGetErrorString(e));
+  dm.release();
+  dout.release();
   return rc;
 }
 

@@ -115,16 +115,24 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
   const bool chainw = warp == KX_PROD;
 
   // ---- ResetOdometer (odometer.cpp:580-609) + points -----------------------------------------------------------------
+  // ResetOdometer runs from the constructor and from Set3Dpoints only (odometer.cpp:153, 173): between the TrackPose
+  // calls of one sample (the chains of run_track_nposes.cpp:232-258) the patch and steepest-descent arrays keep their
+  // contents, so a point that has left the image keeps the template of the last level it was seen at — also from a
+  // PREVIOUS frame step.  With the tracker's "keep_state" the arrays of this CTA (template planes + the per-point sd
+  // coefficients they were made with) are therefore carried through global memory from call to call.
+  float* state = prm.state ? prm.state + (int64_t)t * prm.state_stride : nullptr;
   {
     const float2 z2 = make_float2(0.f, 0.f);
-    for (int e = tid; e < 3 * 32 * P; e += nt) s_ref2[e] = z2;
+    const float2* st2 = reinterpret_cast<const float2*>(state);
+    const bool load = state && prm.state_load;
+    for (int e = tid; e < 3 * 32 * P; e += nt) s_ref2[e] = load ? st2[e] : z2;
     const float* q = prm.pt3d + 3 * off;
     for (int i = tid; i < P; i += nt) {
       s_X[i] = q[i];
       s_Y[i] = q[n_in + i];
       s_Z[i] = q[2 * (int64_t)n_in + i];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) s_AB[i * 12 + k] = 0.0f;
+      for (int k = 0; k < 12; ++k) s_AB[i * 12 + k] = load ? state[3 * 64 * P + i * 12 + k] : 0.0f;
     }
   }
   if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
@@ -375,6 +383,11 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
     if (chainw && lane == 0 && prm.iters) prm.iters[(int64_t)t * (op.lv_f - op.lv_l + 1) + (op.lv_f - sl)] = S.it;
   }
 
+  if (state) {   // the last iteration ended with a CTA barrier: the arrays are quiescent
+    float2* st2 = reinterpret_cast<float2*>(state);
+    for (int e = tid; e < 3 * 32 * P; e += nt) st2[e] = s_ref2[e];
+    for (int e = tid; e < 12 * P; e += nt) state[3 * 64 * P + e] = s_AB[e];
+  }
   if (chainw && lane == 0) {
     getpose_se3(S.p, S.G, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3],
                 prm.p_out + 6 * (int64_t)t);

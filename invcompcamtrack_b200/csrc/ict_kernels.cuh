@@ -54,6 +54,9 @@ struct TrackParams {
   int seq_n, seq_step;             // K2v8 only: seq_n > 1 runs a whole chain in one launch — step k tracks frame
                                    //    fixed_ref + k*seq_step -> + seq_step from pose p_in + 6*T*k to p_out + 6*T*k
                                    //    (iters + T*L*k, npixres + T*k); 0/1: a single step
+  float* state;                    // K2x8 with the tracker's "keep_state": per-track template state carried between calls
+  int64_t state_stride;            //    (floats per track: 3*64 + 12 per point of the largest track), null: reset every call
+  int state_load;                  //    0: the first call after Set3Dpoints (arrays start zeroed, odometer.cpp:173)
   int knob_no_k2r;                 // tracker knob "no_k2r": reference-order psz 32 runs K2x even where K2r applies (A/B, tests)
   int knob_seq_launches;           // tracker knob "seq_launches": a chain is one launch per frame step even where K2v8 could loop
   int tma_ok;                      // every frame of the store carries tensor maps (FrameDesc.tmap)
@@ -122,6 +125,11 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
 cudaError_t launch_ncc(const ict_optparam& op, const CamLevels& cam, const float* img_b, const float* img_r,
                        const float* img_f, int nback, int nfwd, const int64_t* pt_off, int T, const float* pb,
                        const float* pr, const float* pf, float* out, cudaStream_t stream);
+
+// util_getPatch / util_getPatch_grad for npatch centres (mids: x, y pairs) on one level plane set
+cudaError_t launch_get_patches(const float* I, const float* dx, const float* dy, int width, int psz, int pszd2,
+                               int patchnorm, int npatch, const float* mids, float* out_I, float* out_dx, float* out_dy,
+                               cudaStream_t stream);
 
 int64_t launch_count(int reset);
 

@@ -1017,6 +1017,47 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
 }
 
 // ==================================================================================================
+// util_getPatch / util_getPatch_grad (utilities.cpp:55-113, 115-189) for a list of patch centres: one CTA per centre,
+// bilinear samples with the reference's placement (ceil(x + 1e-5f) quirk included) and association order, optional
+// mean subtraction of the INTENSITY patch with Eigen's packet sum (utilities.cpp:111-112, 187-188).
+// planes: bit 0 intensity, bit 1 dx, bit 2 dy.  out_* : [npatch][psz*psz].
+// ==================================================================================================
+__global__ void __launch_bounds__(128) k_get_patches(const float* __restrict__ I, const float* __restrict__ dx,
+                                                     const float* __restrict__ dy, int width, int psz, int pszd2,
+                                                     int patchnorm, const float* __restrict__ mids, float* out_I,
+                                                     float* out_dx, float* out_dy) {
+  const int n = psz * psz;
+  const long long g = blockIdx.x;
+  const float mx = mids[2 * g], my = mids[2 * g + 1];
+  const PatchPlace q = patch_place(mx, my, pszd2, width);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int r = e / psz, c = e - r * psz, ad = q.base + r * width + c;
+    if (out_I) out_I[g * n + e] = bilin4(I, ad, width, q.w0, q.w1, q.w2, q.w3);
+    if (out_dx) out_dx[g * n + e] = bilin4(dx, ad, width, q.w0, q.w1, q.w2, q.w3);
+    if (out_dy) out_dy[g * n + e] = bilin4(dy, ad, width, q.w0, q.w1, q.w2, q.w3);
+  }
+  if (patchnorm && out_I) {
+    __shared__ float s_mean;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float* p = out_I + g * n;
+      s_mean = eigen_sum_serial([&](int e) { return p[e]; }, n) / n;   // tmp_in_e.sum() / novals
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) out_I[g * n + e] = out_I[g * n + e] - s_mean;
+  }
+}
+
+cudaError_t launch_get_patches(const float* I, const float* dx, const float* dy, int width, int psz, int pszd2,
+                               int patchnorm, int npatch, const float* mids, float* out_I, float* out_dx, float* out_dy,
+                               cudaStream_t stream) {
+  if (npatch <= 0) return cudaSuccess;
+  k_get_patches<<<npatch, 128, 0, stream>>>(I, dx, dy, width, psz, pszd2, patchnorm, mids, out_I, out_dx, out_dy);
+  count_launch_external();
+  return cudaGetLastError();
+}
+
+// ==================================================================================================
 // NCC hypothesis scoring, run_track_nposes.cpp:271-355.  One CTA per point; three mean-subtracted psz x psz
 // patches (util_getPatch with dopatchnorm, :281) at level lv_l, each divided by its norm (:317-319),
 // corr = max(0, (max(0,<b,r>)*nback^2 + max(0,<r,f>)*nfwd^2) / (nback^2 + nfwd^2)) (:324-348).

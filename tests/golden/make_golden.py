@@ -9,6 +9,8 @@ oracle/_ref and Python cv2):   python tests/golden/make_golden.py
                   (H, J^T r, delta_p) recorded by the shim's fullPivLu().solve() hook.
   se3.npz         util_SE3_coeff_to_group / util_SE3_group_to_coeff, float and double instantiations (oracle/_ref).
   getpatch.npz    util_getPatch / util_getPatch_grad at awkward centres (integers >= 256, frac > 1-1e-5, odd psz).
+  drivers_stale.npz  run_track_nposes.cpp on a pan in which border points leave the frames mid-chain: pins the state
+                  the reference keeps BETWEEN TrackPose calls (ResetOdometer only runs from Set3Dpoints).
   drivers.npz     inputs and outputs of the reference's own main()s: run_track_nposes.cpp (text in/out, forward and
                   backward chains, NCC) and run_io_reprojection_test.cpp (binary in/out), compiled into oracle/_ref.
 """
@@ -161,6 +163,55 @@ def nposes_inputs():
     return frames, "\n".join(lines) + "\n", sc
 
 
+def nposes_stale_inputs():
+    """run_track_nposes with points that LEAVE the frames mid-chain (state between TrackPose calls): a
+    sideways pan over 6 frames (2 back, 3 forward of the reference frame), half of the correspondences within 12 px of
+    the left / right border of the reference frame, 4 pose samples."""
+    w, h, nb, nf = 160, 120, 2, 3
+    sc = synth.Scene(19, w, h)
+    nfr = nb + nf + 1
+    poses = np.zeros((nfr, 6))
+    for k in range(nfr):                       # pan: ~7 px per frame at level 0, plus a little roll
+        poses[k] = np.array([0.22 * (k - nb), 0.02 * (k - nb), 0.0, 0.0, 0.0, 0.004 * (k - nb)])
+    frames = [sc.render(poses[k]) for k in range(nfr)]
+    rng = np.random.default_rng(14)
+    n = 64
+    u = np.concatenate([rng.uniform(1, 12, n // 4), rng.uniform(w - 12, w - 1, n // 4), rng.uniform(20, w - 20, n // 2)])
+    v = rng.uniform(10, h - 10, n)
+    pts = sc.backproject(u, v, poses[nb]).reshape(3, -1).T
+    samples = []
+    for s_ in range(4):
+        p = poses[nb] + rng.normal(0, 1, 6) * np.array([2e-3, 2e-3, 2e-3, 3e-4, 3e-4, 3e-4]) * (s_ > 0)
+        ids = np.sort(rng.choice(n, size=(40, 48, 36, 44)[s_], replace=False)) + 1
+        samples.append((p, ids))
+    lines = ["2 0 8 10 0.01 0 0 48 0", "%g %g %g %g %d %d" % (sc.fc[0], sc.fc[1], sc.cc[0], sc.cc[1], w, h),
+             "%d %d" % (nb, nf)]
+    lines += ["@DIR@/f%d.pgm" % k for k in range(nfr)]
+    lines.append("%d" % len(pts))
+    lines += ["0 0 %.17g %.17g %.17g" % tuple(x) for x in pts]
+    lines.append("%d" % len(samples))
+    for p, ids in samples:
+        lines.append(" ".join("%.17g" % v_ for v_ in p) + " %d " % len(ids) + " ".join(str(i) for i in ids))
+    return frames, "\n".join(lines) + "\n"
+
+
+def gen_drivers_stale():
+    import subprocess
+    import tempfile
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    frames, template = nposes_stale_inputs()
+    with tempfile.TemporaryDirectory() as d:
+        for k, f in enumerate(frames):
+            write_pgm(os.path.join(d, "f%d.pgm" % k), f)
+        open(os.path.join(d, "in.txt"), "w").write(template.replace("@DIR@", d))
+        subprocess.run([os.path.join(ref_dir, "run_track_nposes"), os.path.join(d, "in.txt"), os.path.join(d, "out.txt")],
+                       check=True)
+        out = open(os.path.join(d, "out.txt")).read()
+    np.savez_compressed(os.path.join(HERE, "drivers_stale.npz"), frames=np.stack(frames), nposes_input=template,
+                        nposes_output=out)
+    print("run_track_nposes (points leaving the frames) golden:\n" + out[:600])
+
+
 def gen_drivers():
     """Golden outputs of the reference's own DRIVERS (oracle/_ref/run_track_nposes, run_io_reprojection_test: the
     reference mains compiled against the stand-in headers; the stand-in imread reads binary PGM)."""
@@ -202,4 +253,5 @@ if __name__ == "__main__":
     gen_se3(ref)
     gen_getpatch(ref)
     gen_drivers()
+    gen_drivers_stale()
     print("golden fixtures written to", HERE)

@@ -254,6 +254,40 @@ def test_several_large_tracks_per_call(ict, orc):
     assert np.abs(g["p_out"] - o["p_out"]).max() < 1e-3, res
 
 
+@pytest.mark.parametrize("psz,patchnorm", [(8, 0), (8, 1), (7, 1), (32, 0), (4, 1)])
+def test_get_patches_equal_the_oracle(ict, orc, psz, patchnorm):
+    """ict_get_patches == util_getPatch / util_getPatch_grad (utilities.cpp:55-189), bit for bit, including the
+    ceil(x + 1e-5f) placement at integer coordinates below and above 256, odd patch sizes and the patch mean in Eigen's
+    summation order."""
+    from invcompcamtrack_b200 import synth
+    from oracle import oracle as O
+    sc, A, B, _ = synth.make_pair(31, 640, 480)
+    lv_f = 2
+    fr = ict.Frames(1, 640, 480, lv_f, psz)
+    fr.upload(0, A[None].astype(np.float32))
+    pyr = orc.pyramid_build(A.astype(np.float32), lv_f, psz)
+    _, off, sw, sh = O.pyramid_layout(640, 480, lv_f, psz)
+    op = ict.make_optparam(lv_f=lv_f, psz=psz, dopatchnorm=patchnorm, maxpttrack=4)
+    op_o = O.make_optparam(lv_f=lv_f, psz=psz, dopatchnorm=patchnorm, maxpttrack=4)
+    rng = np.random.default_rng(5)
+    for lvl in range(lv_f + 1):
+        wl, hl = 640 >> lvl, 480 >> lvl
+        mids = np.concatenate([rng.uniform([0, 0], [wl, hl], (24, 2)),
+                               [[5.0, 7.0], [255.0, 100.0], [256.0, 30.0], [300.0, 17.0], [0.0, 0.0], [wl, hl],
+                                [12.999995, 40.5]]]).astype(np.float32)
+        mids = mids[(mids[:, 0] <= wl) & (mids[:, 1] <= hl)]
+        I, dx, dy = fr.get_patches(0, lvl, op, mids)
+        n = sw[lvl] * sh[lvl]
+        planes = [pyr[k][off[lvl]:off[lvl] + n] for k in range(3)]
+        for i, m in enumerate(mids):
+            ref = orc.getpatch_grad(planes[0], planes[1], planes[2], m, op_o, sw[lvl])
+            assert np.array_equal(I[i], ref[0]) and np.array_equal(dx[i], ref[1]) and np.array_equal(dy[i], ref[2]), (lvl, m)
+        only = fr.get_patches(0, lvl, op, mids, grad=False)
+        for i, m in enumerate(mids[:6]):
+            assert np.array_equal(only[i], orc.getpatch(planes[0], m, op_o, sw[lvl]))
+    fr.close()
+
+
 def test_ncc_scoring(ict, orc):
     """run_track_nposes.cpp:271-355 on the GPU vs the oracle: per-point weighted NCC of back / reference / forward
     patches, including points outside the frames (corr = -1 when the reference point is out, weight 0 otherwise)."""
