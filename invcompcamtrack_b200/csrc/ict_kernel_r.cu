@@ -63,6 +63,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, 
 __device__ __forceinline__ void mbar_expect_tx_only(unsigned long long* b, unsigned bytes) {   // no arrival
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ict_saddr(b)), "r"(bytes) : "memory");
 }
+// Producer-side wait for a window: a few immediate polls (the first units' windows are on the critical path of the
+// iteration), then a short sleep per poll.  A tight try_wait loop of the waiting producers was 20 % of all issued
+// instructions (ncu), on the schedulers the chain warps need.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* b, unsigned parity) {
+  unsigned done = 0;
+  for (int tries = 0;; ++tries) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(ict_saddr(b)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (tries >= 4) __nanosleep(40);
+  }
+}
 // generic-proxy accesses to shared memory (the in-place pdiff stores, the chain warps' loads) ordered before the
 // async-proxy write of the next TMA into the same slot
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -486,7 +505,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
             const int vis = S.nvis[pp];
             if (u >= KR_NSLOT) {          // the slot is still in use by unit u - KR_NSLOT: fetch when it is released
               if (lane == 0) {
-                mbar_wait(&S.slot_free[u - KR_NSLOT], par);
+                mbar_wait_relaxed(&S.slot_free[u - KR_NSLOT], par);
                 if (vis) {
                   fence_proxy_async();
                   mbar_expect_tx(&S.win_full[u], KR_WIN_BYTES);
@@ -500,7 +519,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
             if (vis) {
               const float4 w = S.npl[pp];
               const float* wsh = win + ((S.nx[pp] - 1) & 3);   // the patch's left neighbour column inside the box
-              mbar_wait(&S.win_full[u], par);
+              mbar_wait_backoff(&S.win_full[u], par);
               // The residual rows go back INTO the window (row r of the patch over row r of the window, which only the
               // sample of row r reads), at other word positions than the lanes read: every lane first loads all it
               // needs, the warp synchronises, then it stores — lanes of a warp are not guaranteed to run in lockstep
@@ -590,10 +609,12 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
           for (int j = 0; j < 6; ++j) sumsd[j] = S.sum[j];
           lu6_solve_regs(lu, lu_rank, S.f.pr, S.f.qd, S.sum, S.dp);
           __syncwarp();
+          const long long t_s1 = trace ? clock64() : 0;
 #pragma unroll
           for (int j = 0; j < 6; ++j) { dp[j] = S.dp[j]; pr[j] = S.p[j] + dp[j]; }
           Gr[3] = Gr[7] = Gr[11] = 0.0f;
           se3_exp_f(Gr, pr);
+          const long long t_s2 = trace ? clock64() : 0;
           const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) +
                                (fabsf(dp[4]) + fabsf(dp[5]));           // lpNorm<1>, odometer.cpp:412
           __syncwarp();
@@ -612,6 +633,8 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
               rec[15] = (float)S.nv;
               for (int j = 16; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
               rec[16] = (float)w0;
+              rec[17] = (float)(t_s1 - t_c1);        // redux hand-off + solve
+              if (it != 0) rec[18] = (float)(t_s2 - t_s1);   // pose update + exp
               if (it == 0) {   // first record of a level: cycles of its precompute phases
                 rec[19] = (float)(lt1 - lt0);   // acquires, reference placement, window issue
                 rec[20] = (float)(lt2 - lt1);   // window wait, sampling, sd store

@@ -15,7 +15,9 @@ print("records %d  iterations/track %.1f" % (ok.sum(), ok.sum() / NT))
 print("chain loop cycles: mean %.0f  median %.0f  p10 %.0f p90 %.0f" % (tr[..., 23][ok].mean(), np.median(tr[..., 23][ok]),
       np.percentile(tr[..., 23][ok], 10), np.percentile(tr[..., 23][ok], 90)))
 print("serial section cycles: mean %.0f  median %.0f" % (tr[..., 22][ok].mean(), np.median(tr[..., 22][ok])))
-for k in (16, 17, 18, 19, 20, 21):
+later = ok & (tr[..., 1] > 0)
+print("serial: redux hand-off + solve: mean %.0f   pose update + exp: mean %.0f (iterations > 0)" % (tr[..., 17][ok].mean(), tr[..., 18][later].mean()))
+for k in (16,):
     v = tr[..., k][ok]
     if v.any():
         print("field %d: mean %.0f median %.0f" % (k, v.mean(), np.median(v)))
