@@ -123,6 +123,23 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
  * dopatchnorm, are always warp trees). */
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
 
+/* ---- f4 (next row): robustness modes, opt-in — NOT parity mode ----------------------------------------------------------
+ * Each flag removes one documented quirk of the reference; results then deliberately differ from the
+ * reference's.  Implemented in the fast mode for 8x8 patches (ict_tracker_set_sum_order(tr, 0), K2v8); other
+ * configurations return ICT_ERR_UNSUPPORTED from the tracking calls while a flag is set.
+ *   ICT_ROBUST_FULL_STEP  gradients are I(x+1) - I(x-1), twice the derivative (utilities.cpp:30-31), so every update is
+ *                         half a Gauss-Newton step; this takes the full step (== halved gradients, exactly)
+ *   ICT_ROBUST_COMPOSE    G <- exp(delta_p) * G instead of adding delta_p to the se(3) coefficients (pose.cpp:116-129):
+ *                         the update the steepest-descent images are the derivative of
+ *   ICT_ROBUST_FLOOR      patch origin floor(x) + 1 everywhere instead of ceil(x + 1e-5f) (utilities.cpp:66-69), which is
+ *                         one pixel off for integer coordinates >= 256 and two for frac(x) > 1 - 1e-5
+ * The fourth fix of SURVEY.md §8(f) — no stale template / steepest-descent values for points out of view — is what the
+ * library does unless the knob "keep_state" asks for the reference's behaviour. */
+#define ICT_ROBUST_FULL_STEP 1u
+#define ICT_ROBUST_COMPOSE 2u
+#define ICT_ROBUST_FLOOR 4u
+int ict_tracker_set_robust(ict_tracker* tr, unsigned flags);
+
 /* Explicit switches of a tracker (tests and A/B tools; the library reads no environment variable in its default build):
  *   "no_k2r"       1: reference-order 32x32 tracks run the producer/chain-ring kernel K2x even where K2r (resident
  *                     steepest-descent images, TMA windows) applies — same bits, for comparisons

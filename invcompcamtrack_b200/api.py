@@ -11,6 +11,9 @@ MAX_LEVELS = 8
 _ERR = {1: "ICT_ERR_NO_DEVICE", 2: "ICT_ERR_BAD_ARG", 3: "ICT_ERR_CUDA", 4: "ICT_ERR_NOMEM", 5: "ICT_ERR_UNSUPPORTED"}
 
 
+ROBUST_FULL_STEP, ROBUST_COMPOSE, ROBUST_FLOOR = 1, 2, 4
+
+
 class IctError(RuntimeError):
     pass
 
@@ -61,6 +64,7 @@ SIGNATURES = {
     "ict_tracker_set_sum_order": (C.c_int, [C.c_void_p, C.c_int]),
     "ict_tracker_set_knob": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ict_tracker_set_teacher": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ict_tracker_set_robust": (C.c_int, [C.c_void_p, C.c_uint]),
     "ict_tracker_set_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "ict_tracker_set_points_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_void_p]),
@@ -257,6 +261,10 @@ class Tracker:
         poses = np.ascontiguousarray(poses, np.float32)
         assert poses.ndim == 3 and poses.shape[0] == self.T and poses.shape[2] == 8
         _check(lib().ict_tracker_set_teacher(self.h_, _p(poses), poses.shape[1]))
+
+    def set_robust(self, flags):
+        """ROBUST_FULL_STEP | ROBUST_COMPOSE | ROBUST_FLOOR: opt-in deviations from the reference (ictrack.h)."""
+        _check(lib().ict_tracker_set_robust(self.h_, int(flags)))
 
     def set_knob(self, name, value):
         """Explicit A/B switches: "no_k2r", "seq_launches" (ictrack.h)."""

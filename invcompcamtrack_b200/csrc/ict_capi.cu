@@ -463,6 +463,7 @@ struct ict_tracker {
   int sum_mode = 1;            // the reference's summation order is the default (ictrack.h, ict_tracker_set_sum_order)
   int force_general = 0;
   int knob_no_k2r = 0, knob_seq_launches = 0;   // ict_tracker_set_knob
+  unsigned robust = 0;         // ict_tracker_set_robust
   int keep_state = 0;          // knob "keep_state": template arrays persist between TrackPose calls until the next Set3Dpoints
   bool state_valid = false;
   int seq_n = 0, seq_step = 0;   // set by ict_track_sequence around one run_tracks call (chain in one launch)
@@ -526,6 +527,13 @@ int ict_tracker_set_teacher(ict_tracker* tr, const float* poses, int trace_cap) 
   CU(tr->teacher.reserve(bytes));
   CU(cudaMemcpy(tr->teacher.p, poses, bytes, cudaMemcpyHostToDevice));
   tr->teacher_cap = trace_cap;
+  return ICT_OK;
+}
+
+int ict_tracker_set_robust(ict_tracker* tr, unsigned flags) {
+  if (!tr || (flags & ~(ICT_ROBUST_FULL_STEP | ICT_ROBUST_COMPOSE | ICT_ROBUST_FLOOR)))
+    return fail(ICT_ERR_BAD_ARG, "ict_tracker_set_robust: unknown flag");
+  tr->robust = flags;
   return ICT_OK;
 }
 
@@ -664,6 +672,9 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
   prm.seq_step = tr->seq_step;
   prm.knob_no_k2r = tr->knob_no_k2r;
   prm.knob_seq_launches = tr->knob_seq_launches;
+  prm.robust = tr->robust;
+  if (tr->robust && !(tr->sum_mode == 0 && !tr->force_general && v8_supported(tr->op, tr->max_pts)))
+    return fail(ICT_ERR_UNSUPPORTED, "robustness modes need the fast mode (sum order 0), psz 8 and at most 240 points per track");
   if (tr->keep_state) {
     // carried template state: implemented by the reference-order kernel for 8x8 patches (the drivers' configuration)
     if (!(tr->sum_mode == 1 && !tr->force_general && kx8_supported(tr->op, tr->max_pts)))

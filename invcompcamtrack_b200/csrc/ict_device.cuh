@@ -655,12 +655,15 @@ struct PatchPlace {
   int base;
   float w0, w1, w2, w3;
 };
-__device__ __forceinline__ PatchPlace patch_place(float mx, float my, int pszd2, int width) {
+// consistent == true (ICT_ROBUST_FLOOR, opt-in, not parity): the patch origin is floor(x) + 1 for every x, instead of the
+// reference's ceil(x + 1e-5f), which equals floor(x) for integer x >= 256 and floor(x) + 2 for frac(x) > 1 - 1e-5
+// (SURVEY.md §9.2): template and new-frame patches are then sampled on the same grid wherever their centres fall.
+__device__ __forceinline__ PatchPlace patch_place(float mx, float my, int pszd2, int width, bool consistent = false) {
   PatchPlace q;
-  const int pos0 = (int)ceilf(mx + .00001f);
-  const int pos1 = (int)ceilf(my + .00001f);
   const int pos2 = (int)floorf(mx);
   const int pos3 = (int)floorf(my);
+  const int pos0 = consistent ? pos2 + 1 : (int)ceilf(mx + .00001f);
+  const int pos1 = consistent ? pos3 + 1 : (int)ceilf(my + .00001f);
   const float r0 = mx - (float)pos2;
   const float r1 = my - (float)pos3;
   q.w0 = r0 * r1;

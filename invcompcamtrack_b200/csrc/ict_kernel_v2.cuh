@@ -11,14 +11,15 @@ __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cas
 // project_pt (pose.cpp:307-397) of one point at level intrinsics (fx, fy, cx, cy) + util_getPatch placement
 // (utilities.cpp:65-94): the reference's operation order, no fused operations.  Writes {base, vis, -, -}, {w0..w3}.
 __device__ __forceinline__ int place_point(const float* G, float X, float Y, float Z, float fx, float fy, float cx,
-                                           float cy, float swo, float sho, int width, float4* dst, int pszd2 = 16) {
+                                           float cy, float swo, float sho, int width, float4* dst, int pszd2 = 16,
+                                           bool consistent = false) {
   const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];
   const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
   const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
   const float mx = (tx / tz) * fx + cx, my = (ty / tz) * fy + cy;
   const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);   // odometer.cpp:369-371 (NaN -> outside)
   PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
-  if (vis) pl = patch_place(mx, my, pszd2, width);
+  if (vis) pl = patch_place(mx, my, pszd2, width, consistent);
   dst[0] = make_float4(__int_as_float(pl.base), __int_as_float(vis), 0.0f, 0.0f);
   dst[1] = make_float4(pl.w0, pl.w1, pl.w2, pl.w3);
   return vis;
@@ -54,6 +55,7 @@ struct __align__(16) V2Shared {
   float Hsum[24];
   Lu6 f;
   float lvl_cycles, gather_cycles;
+  float Ex[12], dps[8];    // robustness mode "compose": exp(delta_p) and delta_p of the running iteration
   int cont, it;
 };
 

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
       const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
       PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
       if (vis) {
-        pl = patch_place(mx, my, 4, width);
+        pl = patch_place(mx, my, 4, width, (prm.robust & ICT_ROBUST_FLOOR) != 0);
         float c[10];
         sd_coefs(xc, yc, zc, fx, fy, c);
         float* ab = s_AB + i * 12;       // stale coefficients survive when the point is out of view
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         const int i = warp + NW * lane;
         int v = 0;
         if (lane < V8_MP && i < P)
-          v = place_point(Gr, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4);
+          v = place_point(Gr, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4,
+                          (prm.robust & ICT_ROBUST_FLOOR) != 0);
         nv_w = __popc(__ballot_sync(0xffffffffu, v));
       }
       __syncwarp();
@@ -333,7 +334,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         const float b3 = __shfl_sync(FULL, bk, 3), b4 = __shfl_sync(FULL, bk, 4), b5 = __shfl_sync(FULL, bk, 5);
         const int nv = (int)__shfl_sync(FULL, bk, 6);
         // 9b. delta_p = M * J^T r (Eigen's solve tabulated once per level), 10. p += delta_p, G = exp(p)
-        const float dpk = fmaf(h1.y, b5, fmaf(h1.x, b4, fmaf(h0.w, b3, fmaf(h0.z, b2, fmaf(h0.y, b1, h0.x * b0)))));
+        float dpk = fmaf(h1.y, b5, fmaf(h1.x, b4, fmaf(h0.w, b3, fmaf(h0.z, b2, fmaf(h0.y, b1, h0.x * b0)))));
+        // opt-in robustness modes (ictrack.h, ict_tracker_set_robust; not parity):
+        //   FULL_STEP — the reference's gradients are I(x+1) - I(x-1), twice the derivative (utilities.cpp:30-31), which
+        //   makes H four times and J^T r twice too large: every update is HALF a Gauss-Newton step.  Halving the
+        //   gradients is exactly doubling delta_p.
+        if (prm.robust & ICT_ROBUST_FULL_STEP) dpk = 2.0f * dpk;
         pk = pk + dpk;
         const float* tf = nullptr;     // teacher forcing (tests): continue from the oracle's pose, not from this one
         if (TRACE) {
@@ -351,7 +357,38 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1) k_track_v8(const Tra
         if (lane < 6) S.p[lane] = pk;
         float Gr[12];
         Gr[3] = Gr[7] = Gr[11] = 0.0f;
-        se3_exp_regs(Gr, q0, q1, q2, q3, q4, q5, S.G, S.p);
+        if (prm.robust & ICT_ROBUST_COMPOSE) {
+          //   COMPOSE — the steepest-descent images are derivatives with respect to a twist applied to the CAMERA-FRAME
+          //   points (d Xc / d xi = [I | -[Xc]x], odometer.cpp:306-326), i.e. to G <- exp(delta_p) * G; the reference
+          //   instead adds delta_p to the coefficients of G (pose.cpp:116-129), which agrees to first order only.
+          const float d0 = __shfl_sync(FULL, dpk, 0), d1 = __shfl_sync(FULL, dpk, 1), d2 = __shfl_sync(FULL, dpk, 2);
+          const float d3 = __shfl_sync(FULL, dpk, 3), d4 = __shfl_sync(FULL, dpk, 4), d5 = __shfl_sync(FULL, dpk, 5);
+          float Go[12], Ex[12];
+#pragma unroll
+          for (int j = 0; j < 12; ++j) Go[j] = S.G[j];
+          if (lane < 6) S.dps[lane] = dpk;
+          Ex[3] = Ex[7] = Ex[11] = 0.0f;
+          se3_exp_regs(Ex, d0, d1, d2, d3, d4, d5, S.Ex, S.dps);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) Gr[4 * r + c2] = Ex[4 * r] * Go[c2] + Ex[4 * r + 1] * Go[4 + c2] + Ex[4 * r + 2] * Go[8 + c2];
+            Gr[4 * r + 3] = Ex[4 * r] * Go[3] + Ex[4 * r + 1] * Go[7] + Ex[4 * r + 2] * Go[11] + Ex[4 * r + 3];
+          }
+          __syncwarp();
+          if (lane == 0) {                   // the coefficients of the composed pose, for the output and the trace
+            double Gd[12], pl6[6];           // in double: the float log (acos of the trace) loses half its digits near identity
+#pragma unroll
+            for (int j = 0; j < 12; ++j) Gd[j] = (double)Gr[j];
+            se3_log<double>(pl6, Gd);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) S.p[j] = (float)pl6[j];
+          }
+          __syncwarp();
+          pk = (lane & 7) < 6 ? S.p[lane & 7] : 0.0f;
+        } else {
+          se3_exp_regs(Gr, q0, q1, q2, q3, q4, q5, S.G, S.p);
+        }
         if (it == 0) normdp_init = normdp;
         int cont = (it + 1 < op.maxiter) & ((normdp / normdp_init) > op.normdp_ratio);   // odometer.cpp:344-346
         if (TRACE) {

@@ -57,6 +57,7 @@ struct TrackParams {
   float* state;                    // K2x8 with the tracker's "keep_state": per-track template state carried between calls
   int64_t state_stride;            //    (floats per track: 3*64 + 12 per point of the largest track), null: reset every call
   int state_load;                  //    0: the first call after Set3Dpoints (arrays start zeroed, odometer.cpp:173)
+  unsigned robust;                 // ICT_ROBUST_* flags (ictrack.h): opt-in deviations from the reference, fast mode / psz 8 (K2v8)
   int knob_no_k2r;                 // tracker knob "no_k2r": reference-order psz 32 runs K2x even where K2r applies (A/B, tests)
   int knob_seq_launches;           // tracker knob "seq_launches": a chain is one launch per frame step even where K2v8 could loop
   int tma_ok;                      // every frame of the store carries tensor maps (FrameDesc.tmap)
