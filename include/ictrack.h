@@ -123,6 +123,21 @@ int ict_tracker_set_optparam(ict_tracker* tr, const ict_optparam* op);
  * dopatchnorm, are always warp trees). */
 int ict_tracker_set_sum_order(ict_tracker* tr, int mode);
 
+/* ---- f3 (next row): pose hypotheses from minimal samples, func_ransac_fitcameras_odom.m:29-90 ---------------------------
+ * For each of nsamples minimal samples (sample_idx[4*s + 0..3], 0-based indices into the npts 2D-3D correspondences):
+ * reject degenerate samples (repeated index, three image points collinear), solve the 6-DoF pose from the four points
+ * (damped Gauss-Newton on the reprojection error in fp64 from p_init, left-multiplied twists; the reference calls the
+ * external ASPnP toolbox here, which is not part of its tree), reproject ALL correspondences and mark those within
+ * inlthresh pixels (:48-52); a sample with fewer than four inliers is rejected (:53-57).
+ *   pt2d: double[2*npts] x block, y block (pixels)      pt3d: double[3*npts] X block, Y block, Z block
+ *   out_pose: double[6*nsamples] se(3) coefficients [t, w] (what run_track_nposes reads per sample)
+ *   out_status: int[nsamples] 1 = usable hypothesis      out_ninl: int[nsamples] or NULL
+ *   out_inlmask: uint8[nsamples*npts] or NULL
+ * Host buffers; the work runs on the GPU (one thread per sample for the solve, one CTA per sample for the inliers). */
+int ict_pose_hypotheses(const float fc[2], const float cc[2], int npts, const double* pt2d, const double* pt3d, int nsamples,
+                        const int* sample_idx, const double p_init[6], double inlthresh, int maxiter, double* out_pose,
+                        int* out_status, int* out_ninl, unsigned char* out_inlmask);
+
 /* ---- f4 (next row): robustness modes, opt-in — NOT parity mode ----------------------------------------------------------
  * Each flag removes one documented quirk of the reference; results then deliberately differ from the
  * reference's.  Implemented in the fast mode for 8x8 patches (ict_tracker_set_sum_order(tr, 0), K2v8); other

@@ -82,6 +82,8 @@ SIGNATURES = {
     "ict_tracker_get_2dpoints": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ict_track_pair": (C.c_int, [C.POINTER(OptParam), _f, _f, _i, _f, _f, _d, C.c_int, _d, _d, C.c_void_p,
                                  C.c_void_p, C.c_int]),
+    "ict_pose_hypotheses": (C.c_int, [_f, _f, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ict_get_patches": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(OptParam), C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "ict_ncc_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -330,6 +332,22 @@ class Tracker:
         _check(lib().ict_ncc_score(self.h_, frames.h_, frame_b, frame_r, frame_f, nback, nfwd, _p(pb), _p(pr), _p(pf),
                                    _p(out)))
         return out
+
+
+def pose_hypotheses(fc, cc, pt2d, pt3d, sample_idx, p_init, inlthresh, maxiter=30):
+    """func_ransac_fitcameras_odom.m:29-90 on the GPU: pt2d [2, n], pt3d [3, n], sample_idx [S, 4] (0-based).
+    Returns dict(pose [S, 6], status [S], ninl [S], mask [S, n])."""
+    fc = np.asarray(fc, np.float32); cc = np.asarray(cc, np.float32)
+    pt2d = np.ascontiguousarray(pt2d, np.float64); pt3d = np.ascontiguousarray(pt3d, np.float64)
+    n = pt2d.shape[1]
+    assert pt2d.shape == (2, n) and pt3d.shape == (3, n)
+    idx = np.ascontiguousarray(sample_idx, np.int32).reshape(-1, 4)
+    S = idx.shape[0]
+    p_init = np.ascontiguousarray(p_init, np.float64)
+    pose = np.zeros((S, 6)); status = np.zeros(S, np.int32); ninl = np.zeros(S, np.int32); mask = np.zeros((S, n), np.uint8)
+    _check(lib().ict_pose_hypotheses(fc.ctypes.data_as(_f), cc.ctypes.data_as(_f), n, _p(pt2d), _p(pt3d), S, _p(idx), _p(p_init),
+                                     float(inlthresh), int(maxiter), _p(pose), _p(status), _p(ninl), _p(mask)))
+    return dict(pose=pose, status=status, ninl=ninl, mask=mask)
 
 
 def track_pair(op, fc, cc, wh, imgA, imgB, pts_soa, p_in, trace_cap=0):

@@ -891,6 +891,41 @@ int ict_track_pair(const ict_optparam* op, const float fc[2], const float cc[2],
   return rc;
 }
 
+int ict_pose_hypotheses(const float fc[2], const float cc[2], int npts, const double* pt2d, const double* pt3d, int nsamples,
+                        const int* sample_idx, const double p_init[6], double inlthresh, int maxiter, double* out_pose,
+                        int* out_status, int* out_ninl, unsigned char* out_inlmask) {
+  if (require_device()) return ICT_ERR_NO_DEVICE;
+  if (!fc || !cc || !pt2d || !pt3d || !sample_idx || !p_init || !out_pose || !out_status || npts < 4 || nsamples < 0 ||
+      !(inlthresh > 0) || maxiter < 1)
+    return fail(ICT_ERR_BAD_ARG, "ict_pose_hypotheses: bad argument");
+  if (nsamples == 0) return ICT_OK;
+  DevBuf d2, d3, ds, dp, dst, dn, dm;
+  cudaError_t e = d2.reserve(sizeof(double) * 2 * npts);
+  if (e == cudaSuccess) e = d3.reserve(sizeof(double) * 3 * npts);
+  if (e == cudaSuccess) e = ds.reserve(sizeof(int) * 4 * (size_t)nsamples);
+  if (e == cudaSuccess) e = dp.reserve(sizeof(double) * 6 * (size_t)nsamples);
+  if (e == cudaSuccess) e = dst.reserve(sizeof(int) * (size_t)nsamples);
+  if (e == cudaSuccess) e = dn.reserve(sizeof(int) * (size_t)nsamples);
+  if (e == cudaSuccess) e = dm.reserve((size_t)nsamples * npts);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d2.p, pt2d, sizeof(double) * 2 * npts, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d3.p, pt3d, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ds.p, sample_idx, sizeof(int) * 4 * (size_t)nsamples, cudaMemcpyHostToDevice, 0);
+  const double fcd[2] = {fc[0], fc[1]}, ccd[2] = {cc[0], cc[1]};
+  if (e == cudaSuccess)
+    e = launch_hypotheses(fcd, ccd, npts, d2.as<double>(), d3.as<double>(), nsamples, ds.as<int>(), p_init, inlthresh, maxiter,
+                          dp.as<double>(), dst.as<int>(), dn.as<int>(), dm.as<unsigned char>(), 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_pose, dp.p, sizeof(double) * 6 * (size_t)nsamples, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_status, dst.p, sizeof(int) * (size_t)nsamples, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess && out_ninl) e = cudaMemcpyAsync(out_ninl, dn.p, sizeof(int) * (size_t)nsamples, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess && out_inlmask) e = cudaMemcpyAsync(out_inlmask, dm.p, (size_t)nsamples * npts, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  int rc = ICT_OK;
+  if (e != cudaSuccess) rc = fail(ICT_ERR_CUDA, std::string("ict_pose_hypotheses: ") + cudaGetErrorString(e));
+  DevBuf* all[] = {&d2, &d3, &ds, &dp, &dst, &dn, &dm};
+  for (DevBuf* b : all) b->release();
+  return rc;
+}
+
 int ict_get_patches(const ict_frames* fs, int frame, int level, const ict_optparam* op, int npatch, const float* mids,
                     float* out_I, float* out_dx, float* out_dy) {
   if (!fs || !op || !mids || npatch < 0) return fail(ICT_ERR_BAD_ARG, "ict_get_patches: null argument");

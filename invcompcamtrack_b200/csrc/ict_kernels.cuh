@@ -132,6 +132,11 @@ cudaError_t launch_get_patches(const float* I, const float* dx, const float* dy,
                                int patchnorm, int npatch, const float* mids, float* out_I, float* out_dx, float* out_dy,
                                cudaStream_t stream);
 
+// f3: pose hypotheses from minimal 4-point samples + inlier sets (ict_hypotheses.cu); all pointers device memory
+cudaError_t launch_hypotheses(const double fc[2], const double cc[2], int npts, const double* pt2d, const double* pt3d,
+                              int nsamples, const int* sample, const double p_init[6], double inlthresh, int maxiter,
+                              double* pose, int* status, int* ninl, unsigned char* mask, cudaStream_t stream);
+
 int64_t launch_count(int reset);
 
 }  // namespace ict
