@@ -41,51 +41,42 @@ __device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
 // evaluated in double and narrowed on assignment (see oracle/ictrack_oracle.c, DEF_SE3_EXP).
 template <typename T>
 __device__ __forceinline__ void se3_exp(T* G, const T* p) {
-  T ra1 = p[3] * p[3];
-  T ra2 = p[4] * p[4];
-  T ra3 = p[5] * p[5];
-  T sig = (T)sqrt((double)(T)(ra1 + ra2 + ra3));
-  T sa, sb, sc;
-  T sigsq2 = (sig * sig);
-  T sigsq3 = (sig * sig * sig);
+  const T wx = p[3], wy = p[4], wz = p[5];
+  const T xx = wx * wx, yy = wy * wy, zz = wz * wz;
+  const T sig = (T)sqrt((double)(T)(xx + yy + zz));
+  T sa, sb, sc;   // sin(s)/s, (1 - cos s)/s^2, (s - sin s)/s^3
+  const T s2 = (sig * sig);
+  const T s3 = (sig * sig * sig);
   if ((double)sig > ICT_LIEALG_SIGTHRESH) {
     double sn, cs;
     sincos_small((double)sig, &sn, &cs);
     sa = (T)(sn / (double)sig);
-    sb = (T)((1 - cs) / (double)sigsq2);
-    sc = (T)(((double)sig - sn) / (double)sigsq3);
+    sb = (T)((1 - cs) / (double)s2);
+    sc = (T)(((double)sig - sn) / (double)s3);
   } else {
-    sa = 1 - sigsq2 / 6 * (1 - sigsq2 / 20 * (1 - sigsq2 / 42));
-    sb = (T)(.5 * (double)(T)(1 - sigsq2 / 12 * (1 - sigsq2 / 30 * (1 - sigsq2 / 56))));
-    sc = (1 - sigsq2 / 20 * (1 - sigsq2 / 42 * (1 - sigsq2 / 72))) / 6;
+    sa = 1 - s2 / 6 * (1 - s2 / 20 * (1 - s2 / 42));
+    sb = (T)(.5 * (double)(T)(1 - s2 / 12 * (1 - s2 / 30 * (1 - s2 / 56))));
+    sc = (1 - s2 / 20 * (1 - s2 / 42 * (1 - s2 / 72))) / 6;
   }
-  T tmp1 = ra2 * sb;
-  T tmp2 = ra3 * sb;
-  T tmp3 = ra1 * sb;
-  T tmp4 = p[3] * p[4] * sb;
-  T tmp5 = p[5] * sa;
-  T tmp6 = p[3] * p[5] * sb;
-  T tmp7 = p[4] * sa;
-  T tmp8 = p[3] * sa;
-  T tmp9 = p[4] * p[5] * sb;
-  G[0] = 1 - tmp1 - tmp2;
-  G[1] = tmp4 - tmp5;
-  G[2] = tmp7 + tmp6;
-  G[4] = tmp5 + tmp4;
-  G[5] = 1 - tmp3 - tmp2;
-  G[6] = tmp9 - tmp8;
-  G[8] = tmp6 - tmp7;
-  G[9] = tmp8 + tmp9;
-  G[10] = 1 - tmp3 - tmp1;
-  tmp1 = p[5] * sb;
-  tmp2 = p[3] * p[4] * sc;
-  tmp3 = p[4] * sb;
-  tmp4 = p[3] * p[5] * sc;
-  tmp5 = p[3] * sb;
-  tmp6 = p[4] * p[5] * sc;
-  G[3] = (1 - (ra2 + ra3) * sc) * p[0] + (tmp2 - tmp1) * p[1] + (tmp3 + tmp4) * p[2];
-  G[7] = (tmp1 + tmp2) * p[0] + (1 - (ra1 + ra3) * sc) * p[1] + (tmp6 - tmp5) * p[2];
-  G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
+  // rotation block R = I + sa [w]x + sb [w]x^2, entry by entry in the reference's association
+  const T yyb = yy * sb, zzb = zz * sb, xxb = xx * sb;
+  const T xyb = wx * wy * sb, xzb = wx * wz * sb, yzb = wy * wz * sb;
+  const T xa = wx * sa, ya = wy * sa, za = wz * sa;
+  G[0] = 1 - yyb - zzb;
+  G[1] = xyb - za;
+  G[2] = ya + xzb;
+  G[4] = za + xyb;
+  G[5] = 1 - xxb - zzb;
+  G[6] = yzb - xa;
+  G[8] = xzb - ya;
+  G[9] = xa + yzb;
+  G[10] = 1 - xxb - yyb;
+  // translation block V u, V = I + sb [w]x + sc [w]x^2
+  const T xb = wx * sb, yb = wy * sb, zb = wz * sb;
+  const T xyc = wx * wy * sc, xzc = wx * wz * sc, yzc = wy * wz * sc;
+  G[3] = (1 - (yy + zz) * sc) * p[0] + (xyc - zb) * p[1] + (yb + xzc) * p[2];
+  G[7] = (zb + xyc) * p[0] + (1 - (xx + zz) * sc) * p[1] + (yzc - xb) * p[2];
+  G[11] = (xzc - yb) * p[0] + (xb + yzc) * p[1] + (1 - (xx + yy) * sc) * p[2];
 }
 
 
@@ -95,52 +86,56 @@ __device__ __forceinline__ void se3_exp(T* G, const T* p) {
 // double-precision root costs ~100 dependent cycles on the thread every other warp of the CTA waits for.  Everything
 // else — the double sin/cos, the three double quotients with their cancellation, the float rotation and translation
 // blocks — is the reference's formula, operation by operation (utilities.h:84-145).
+// ONE_LANE: called by all lanes of a converged warp with the same p; the double-precision block (sin, cos, three
+// quotients: ~100 FP64 instructions, which this GPU issues at a small fraction of the FP32 rate per ACTIVE lane)
+// runs on lane 0 only and its three float results are broadcast.  Same operations, same bits.
+template <bool ONE_LANE = false>
 __device__ __forceinline__ void se3_exp_f(float* G, const float* p) {
-  const float ra1 = p[3] * p[3];
-  const float ra2 = p[4] * p[4];
-  const float ra3 = p[5] * p[5];
-  const float sig = sqrtf(ra1 + ra2 + ra3);
-  float sa, sb, sc;
-  const float sigsq2 = (sig * sig);
-  const float sigsq3 = (sig * sig * sig);
+  const float wx = p[3], wy = p[4], wz = p[5];
+  const float xx = wx * wx, yy = wy * wy, zz = wz * wz;
+  const float sig = sqrtf(xx + yy + zz);
+  float sa, sb, sc;   // sin(s)/s, (1 - cos s)/s^2, (s - sin s)/s^3
+  const float s2 = (sig * sig);
+  const float s3 = (sig * sig * sig);
   if ((double)sig > ICT_LIEALG_SIGTHRESH) {
-    double sn, cs;
-    sincos_small((double)sig, &sn, &cs);
-    sa = (float)(sn / (double)sig);
-    sb = (float)((1 - cs) / (double)sigsq2);
-    sc = (float)(((double)sig - sn) / (double)sigsq3);
+    if (!ONE_LANE || (threadIdx.x & 31) == 0) {
+      double sn, cs;
+      sincos_small((double)sig, &sn, &cs);
+      sa = (float)(sn / (double)sig);
+      sb = (float)((1 - cs) / (double)s2);
+      sc = (float)(((double)sig - sn) / (double)s3);
+    } else {
+      sa = sb = sc = 0.0f;
+    }
+    if (ONE_LANE) {
+      sa = __shfl_sync(0xffffffffu, sa, 0);
+      sb = __shfl_sync(0xffffffffu, sb, 0);
+      sc = __shfl_sync(0xffffffffu, sc, 0);
+    }
   } else {
-    sa = 1 - sigsq2 / 6 * (1 - sigsq2 / 20 * (1 - sigsq2 / 42));
-    sb = (float)(.5 * (double)(float)(1 - sigsq2 / 12 * (1 - sigsq2 / 30 * (1 - sigsq2 / 56))));
-    sc = (1 - sigsq2 / 20 * (1 - sigsq2 / 42 * (1 - sigsq2 / 72))) / 6;
+    sa = 1 - s2 / 6 * (1 - s2 / 20 * (1 - s2 / 42));
+    sb = (float)(.5 * (double)(float)(1 - s2 / 12 * (1 - s2 / 30 * (1 - s2 / 56))));
+    sc = (1 - s2 / 20 * (1 - s2 / 42 * (1 - s2 / 72))) / 6;
   }
-  float tmp1 = ra2 * sb;
-  float tmp2 = ra3 * sb;
-  float tmp3 = ra1 * sb;
-  float tmp4 = p[3] * p[4] * sb;
-  float tmp5 = p[5] * sa;
-  float tmp6 = p[3] * p[5] * sb;
-  float tmp7 = p[4] * sa;
-  float tmp8 = p[3] * sa;
-  float tmp9 = p[4] * p[5] * sb;
-  G[0] = 1 - tmp1 - tmp2;
-  G[1] = tmp4 - tmp5;
-  G[2] = tmp7 + tmp6;
-  G[4] = tmp5 + tmp4;
-  G[5] = 1 - tmp3 - tmp2;
-  G[6] = tmp9 - tmp8;
-  G[8] = tmp6 - tmp7;
-  G[9] = tmp8 + tmp9;
-  G[10] = 1 - tmp3 - tmp1;
-  tmp1 = p[5] * sb;
-  tmp2 = p[3] * p[4] * sc;
-  tmp3 = p[4] * sb;
-  tmp4 = p[3] * p[5] * sc;
-  tmp5 = p[3] * sb;
-  tmp6 = p[4] * p[5] * sc;
-  G[3] = (1 - (ra2 + ra3) * sc) * p[0] + (tmp2 - tmp1) * p[1] + (tmp3 + tmp4) * p[2];
-  G[7] = (tmp1 + tmp2) * p[0] + (1 - (ra1 + ra3) * sc) * p[1] + (tmp6 - tmp5) * p[2];
-  G[11] = (tmp4 - tmp3) * p[0] + (tmp5 + tmp6) * p[1] + (1 - (ra1 + ra2) * sc) * p[2];
+  // rotation block R = I + sa [w]x + sb [w]x^2, entry by entry in the reference's association
+  const float yyb = yy * sb, zzb = zz * sb, xxb = xx * sb;
+  const float xyb = wx * wy * sb, xzb = wx * wz * sb, yzb = wy * wz * sb;
+  const float xa = wx * sa, ya = wy * sa, za = wz * sa;
+  G[0] = 1 - yyb - zzb;
+  G[1] = xyb - za;
+  G[2] = ya + xzb;
+  G[4] = za + xyb;
+  G[5] = 1 - xxb - zzb;
+  G[6] = yzb - xa;
+  G[8] = xzb - ya;
+  G[9] = xa + yzb;
+  G[10] = 1 - xxb - yyb;
+  // translation block V u, V = I + sb [w]x + sc [w]x^2
+  const float xb = wx * sb, yb = wy * sb, zb = wz * sb;
+  const float xyc = wx * wy * sc, xzc = wx * wz * sc, yzc = wy * wz * sc;
+  G[3] = (1 - (yy + zz) * sc) * p[0] + (xyc - zb) * p[1] + (yb + xzc) * p[2];
+  G[7] = (zb + xyc) * p[0] + (1 - (xx + zz) * sc) * p[1] + (yzc - xb) * p[2];
+  G[11] = (xzc - yb) * p[0] + (xb + yzc) * p[1] + (1 - (xx + yy) * sc) * p[2];
 }
 
 // Production-kernel form of the float instantiation above.  sin(s)/s, (1-cos s)/s^2 and (s-sin s)/s^3 are even power
@@ -203,57 +198,45 @@ __device__ __forceinline__ void se3_exp_f32_series(float* G, const float* p) {
 // ---- util_SE3_group_to_coeff<T>, utilities.h:149-241 --------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void se3_log(T* p, const T* G) {
-  T trace = G[0] + G[5] + G[10];
-  T theta = (T)acos((double)(T)(0.5f * (trace - 1)));
-  T oh[9], ohs[9], V[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { oh[k] = 0; ohs[k] = 0; }
+  const T tr = G[0] + G[5] + G[10];
+  const T theta = (T)acos((double)(T)(0.5f * (tr - 1)));
+  // W = theta / (2 sin theta) (R - R^T) = [[0, a, b], [-a, 0, c], [-b, -c, 0]];  Q = W^2 (symmetric: 6 entries)
+  T a = 0, b = 0, c = 0;
+  T q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0;
   if ((double)theta < ICT_LIEALG_EPSILON) {
     p[3] = 0.0f;
     p[4] = 0.0f;
     p[5] = 0.0f;
   } else {
-    T coef = (T)((double)theta / ((double)2.0f * sin((double)theta)));
-    oh[1] = coef * (G[1] - G[4]);
-    oh[3] = -oh[1];
-    oh[2] = coef * (G[2] - G[8]);
-    oh[6] = -oh[2];
-    oh[5] = coef * (G[6] - G[9]);
-    oh[7] = -oh[5];
-    p[3] = -oh[5];
-    p[4] = oh[2];
-    p[5] = -oh[1];
-    T omsq1 = oh[1] * oh[1];
-    T omsq2 = oh[2] * oh[2];
-    T omsq3 = oh[5] * oh[5];
-    ohs[0] = -omsq1 - omsq2;
-    ohs[1] = -oh[2] * oh[5];
-    ohs[3] = ohs[1];
-    ohs[2] = oh[1] * oh[5];
-    ohs[6] = ohs[2];
-    ohs[4] = -omsq1 - omsq3;
-    ohs[5] = -oh[1] * oh[2];
-    ohs[7] = ohs[5];
-    ohs[8] = -omsq2 - omsq3;
+    const T half_over_sinc = (T)((double)theta / ((double)2.0f * sin((double)theta)));
+    a = half_over_sinc * (G[1] - G[4]);
+    b = half_over_sinc * (G[2] - G[8]);
+    c = half_over_sinc * (G[6] - G[9]);
+    p[3] = -c;
+    p[4] = b;
+    p[5] = -a;
+    const T aa = a * a, bb = b * b, cc = c * c;
+    q00 = -aa - bb;
+    q01 = -b * c;
+    q02 = a * c;
+    q11 = -aa - cc;
+    q12 = -a * b;
+    q22 = -bb - cc;
   }
-  T th;
+  T th;   // (1 - (theta/2) / tan(theta/2)) / theta^2
   if ((double)theta < ICT_LIEALG_SIGTHRESH)
     th = 1.0f / 12.0f;
   else
     th = (T)(((double)1.0f - (double)theta / ((double)2.0f * tan((double)(T)(theta / 2.0f)))) /
              (double)(T)(theta * theta));
-  V[0] = 1.0f + th * ohs[0];
-  V[1] = -0.5f * oh[1] + th * ohs[1];
-  V[2] = -0.5f * oh[2] + th * ohs[2];
-  V[3] = -0.5f * oh[3] + th * ohs[3];
-  V[4] = 1.0f + th * ohs[4];
-  V[5] = -0.5f * oh[5] + th * ohs[5];
-  V[6] = -0.5f * oh[6] + th * ohs[6];
-  V[7] = -0.5f * oh[7] + th * ohs[7];
-  V[8] = 1.0f + th * ohs[8];
-  p[0] = V[0] * G[3] + V[1] * G[7] + V[2] * G[11];
-  p[1] = V[3] * G[3] + V[4] * G[7] + V[5] * G[11];
-  p[2] = V[6] * G[3] + V[7] * G[7] + V[8] * G[11];
+  // u = (I - W/2 + th Q) t, row by row
+  const T na = -a, nb = -b, nc = -c;
+  const T v00 = 1.0f + th * q00, v01 = -0.5f * a + th * q01, v02 = -0.5f * b + th * q02;
+  const T v10 = -0.5f * na + th * q01, v11 = 1.0f + th * q11, v12 = -0.5f * c + th * q12;
+  const T v20 = -0.5f * nb + th * q02, v21 = -0.5f * nc + th * q12, v22 = 1.0f + th * q22;
+  p[0] = v00 * G[3] + v01 * G[7] + v02 * G[11];
+  p[1] = v10 * G[3] + v11 * G[7] + v12 * G[11];
+  p[2] = v20 * G[3] + v21 * G[7] + v22 * G[11];
 }
 
 // ---- PoseClass::setpose_se3, pose.cpp:25-76 -------------------------------------------------------------------

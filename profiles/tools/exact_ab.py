@@ -26,7 +26,7 @@ p_in = np.zeros((NT, 6))
 
 
 def run(order, knob=None, trace_cap=0):
-    tr.set_knob("no_k2r", 1 if knob else 0)
+    tr.set_knob("no_k2r", 1 if knob == "no_k2r" else 0)
     tr.set_sum_order(order)
     ts = []
     out = None
@@ -51,7 +51,7 @@ for name, order, knob in (("K2r", 1, None), ("K2x", 1, "no_k2r"), ("K2v2", 0, No
     out, dt = run(order, knob)
     res[name] = out
     npx = int(out["npixres"].sum())
-    print("%-5s %8.3f ms  %.3e pixel-residuals/s  %.3e tracks/s  iters/track %.1f" %
+    print("%-22s %8.3f ms  %.3e pixel-residuals/s  %.3e tracks/s  iters/track %.1f" %
           (name, dt * 1e3, npx / dt, NT / dt, out["iters"].sum(axis=1).mean()), flush=True)
 assert np.array_equal(res["K2r"]["p_out"], res["K2x"]["p_out"]) and np.array_equal(res["K2r"]["iters"], res["K2x"]["iters"])
 print("K2r == K2x on all %d tracks" % NT)
