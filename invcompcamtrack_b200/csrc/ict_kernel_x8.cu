@@ -48,24 +48,47 @@ __device__ __forceinline__ float x8_patch_sum(float a, float b) {
   return __shfl_sync(FULL, r, 24);
 }
 
-// chain warp, one staged patch: chain (k, c) adds rows 0..7 of column c
-__device__ __forceinline__ void x8_consume(const float* tile, int lane, bool first, float& sx, float& sy) {
+// chain warp, one round of staged patches: chain (k, c) adds rows 0..7 of column c, patch after patch.  The quads of
+// patch w + 1 are loaded before the sixteen dependent additions of patch w, so that their latency (and the shared-
+// memory pipe's four cycles per LDS.128) is covered by the additions instead of preceding them.
+struct X8Quads {
+  float4 x0, x1, y0, y1;
+};
+__device__ __forceinline__ void x8_load(const float* tile, int lane, X8Quads& q) {
   const int c = lane & 7, kx = lane >> 3;
   const float4* px = reinterpret_cast<const float4*>(tile + (kx * 8 + c) * 8);
   const float4* py = reinterpret_cast<const float4*>(tile + ((4 + kx) * 8 + c) * 8);
-  const float4 x0 = px[0], x1 = px[1];
-  float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
-  if (lane < 16) { y0 = py[0]; y1 = py[1]; }
-  sx = first ? x0.x : sx + x0.x;  sy = first ? y0.x : sy + y0.x;
-  sx = sx + x0.y; sy = sy + y0.y; sx = sx + x0.z; sy = sy + y0.z; sx = sx + x0.w; sy = sy + y0.w;
-  sx = sx + x1.x; sy = sy + y1.x; sx = sx + x1.y; sy = sy + y1.y; sx = sx + x1.z; sy = sy + y1.z; sx = sx + x1.w; sy = sy + y1.w;
+  // a column's eight rows are 32 bytes: columns c and c + 4 share their banks, so columns 4..7 keep their two row
+  // quads swapped (x8_store) — the eight lanes of an LDS.128 phase then cover all 32 banks
+  const int lo = (c >> 2) & 1;
+  q.x0 = px[lo];
+  q.x1 = px[lo ^ 1];
+  q.y0 = q.y1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < 16) { q.y0 = py[lo]; q.y1 = py[lo ^ 1]; }
 }
+__device__ __forceinline__ void x8_add(const X8Quads& q, bool first, float& sx, float& sy) {
+  sx = first ? q.x0.x : sx + q.x0.x;  sy = first ? q.y0.x : sy + q.y0.x;
+  sx = sx + q.x0.y; sy = sy + q.y0.y; sx = sx + q.x0.z; sy = sy + q.y0.z; sx = sx + q.x0.w; sy = sy + q.y0.w;
+  sx = sx + q.x1.x; sy = sy + q.y1.x; sx = sx + q.x1.y; sy = sy + q.y1.y; sx = sx + q.x1.z; sy = sy + q.y1.z; sx = sx + q.x1.w; sy = sy + q.y1.w;
+}
+template <int NP>
 __device__ __forceinline__ void x8_consume_round(const float* half, int lane, int j, int ntile, float& sx, float& sy) {
-  if ((j + 1) * KX_PROD <= ntile) {
+  X8Quads cur, nxt;
+  x8_load(half, lane, cur);
+  if ((j + 1) * NP <= ntile) {
 #pragma unroll
-    for (int w = 0; w < KX_PROD; ++w) x8_consume(half + w * X8_TILE, lane, w == 0 && j == 0, sx, sy);
+    for (int w = 0; w < NP; ++w) {
+      if (w + 1 < NP) x8_load(half + (w + 1) * X8_TILE, lane, nxt);
+      x8_add(cur, w == 0 && j == 0, sx, sy);
+      cur = nxt;
+    }
   } else {
-    for (int w = 0; j * KX_PROD + w < ntile; ++w) x8_consume(half + w * X8_TILE, lane, w == 0 && j == 0, sx, sy);
+    const int n = ntile - j * NP;
+    for (int w = 0; w < n; ++w) {
+      if (w + 1 < n) x8_load(half + (w + 1) * X8_TILE, lane, nxt);
+      x8_add(cur, w == 0 && j == 0, sx, sy);
+      cur = nxt;
+    }
   }
 }
 
@@ -73,15 +96,19 @@ __device__ __forceinline__ void x8_consume_round(const float* half, int lane, in
 __device__ __forceinline__ void x8_store(float* tile, int q, int c, const float* v0, const float* v1) {
 #pragma unroll
   for (int k = 0; k < 6; ++k)
-    *reinterpret_cast<float2*>(tile + (k * 8 + c) * 8 + 2 * q) = make_float2(v0[k], v1[k]);
+    *reinterpret_cast<float2*>(tile + (k * 8 + c) * 8 + ((2 * q) ^ (c & 4))) = make_float2(v0[k], v1[k]);
 }
 
-template <bool PN>
-__global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
+// NP producer warps + the chain warp.  NP = 7: 256 threads, two CTAs per SM up to 100 points per track (throughput form).
+// NP = 15: 512 threads, one CTA per SM — a producer's round is ~150 dependent unfused instructions (~900 cycles), so
+// the time of an iteration is rounds x 900 and twice the producers halve it; chosen when only one CTA fits an SM anyway
+// or when the batch is too small to fill the GPU twice (the reference's own use: one track per call).
+template <bool PN, int NP>
+__global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(const TrackParams prm) {
   constexpr int N = 64;
   extern __shared__ __align__(16) float smem[];
   __shared__ KxShared S;
-  __shared__ int s_nv[8];
+  __shared__ int s_nv[NP + 1];
 
   const int t = blockIdx.x + prm.t0;
   const ict_optparam& op = prm.op;
@@ -92,13 +119,13 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
   const bool donorm = op.donorm != 0;
   const bool pnorm = PN && op.dopatchnorm != 0;
   const int q2 = lane >> 3, cc = lane & 7;
-  const int ROUNDS = (P + KX_PROD - 1) / KX_PROD;
+  const int ROUNDS = (P + NP - 1) / NP;
 
   float2* s_ref2 = reinterpret_cast<float2*>(smem);    // [P][32]: (row 2q, row 2q+1) of column c, lane = 8q + c
   float2* s_gx2 = s_ref2 + 32 * P;
   float2* s_gy2 = s_gx2 + 32 * P;
-  float* s_ring = reinterpret_cast<float*>(s_gy2 + 32 * P);   // [2][KX_PROD][X8_TILE]
-  float4* s_rpl = reinterpret_cast<float4*>(s_ring + 2 * KX_PROD * X8_TILE);   // [P][2] reference placement
+  float* s_ring = reinterpret_cast<float*>(s_gy2 + 32 * P);   // [2][NP][X8_TILE]
+  float4* s_rpl = reinterpret_cast<float4*>(s_ring + 2 * NP * X8_TILE);   // [P][2] reference placement
   float4* s_npl = s_rpl + 2 * P;                        // [P][2] new-frame placement
   float* s_AB = reinterpret_cast<float*>(s_npl + 2 * P);    // [P][12]
   float* s_X = s_AB + 12 * P;
@@ -112,7 +139,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
   const int nf = prm.new_frame ? prm.new_frame[t] : prm.fixed_new;
   const FrameDesc* fr_ref = prm.frames + rf;
   const FrameDesc* fr_new = prm.frames + nf;
-  const bool chainw = warp == KX_PROD;
+  const bool chainw = warp == NP;
 
   // ---- ResetOdometer (odometer.cpp:580-609) + points -----------------------------------------------------------------
   // ResetOdometer runs from the constructor and from Set3Dpoints only (odometer.cpp:153, 173): between the TrackPose
@@ -137,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
   }
   if (tid == 0) setpose_se3(prm.p_in + 6 * (int64_t)t, donorm, prm.norm + 4 * (int64_t)t, prm.norm[4 * (int64_t)t + 3], S.p, S.G);
   if (tid >= 32 && tid < 34) {
-    mbar_init(&S.full[tid - 32], 32 * KX_PROD);
+    mbar_init(&S.full[tid - 32], 32 * NP);
     mbar_init(&S.empty[tid - 32], 32);
   }
   __syncthreads();
@@ -191,7 +218,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
     }
     __syncthreads();
     // ---- 4b. template gather (all eight warps; util_getPatch_grad, unfused, reference order) ------------------------
-    for (int i = warp; i < P; i += 8) {
+    for (int i = warp; i < P; i += NP + 1) {
       const float4 pa = s_rpl[2 * i], pw = s_rpl[2 * i + 1];
       if (__float_as_int(pa.y)) {
         const int o = __float_as_int(pa.x) + (2 * q2 - 1) * width + cc;
@@ -216,7 +243,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1, use = ground >> 1;
           if (use > 0) mbar_wait_relaxed(&S.empty[h], (use - 1) & 1);
-          const int i = j * KX_PROD + warp;
+          const int i = j * NP + warp;
           if (i < P) {
             const float2 GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
             float ab[12];
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
               case 2: kx_hess_products<2>(sd0, v0); kx_hess_products<2>(sd1, v1); break;
               default: kx_hess_products<3>(sd0, v0); kx_hess_products<3>(sd1, v1); break;
             }
-            x8_store(s_ring + (h * KX_PROD + warp) * X8_TILE, q2, cc, v0, v1);
+            x8_store(s_ring + (h * NP + warp) * X8_TILE, q2, cc, v0, v1);
           }
           mbar_arrive(&S.full[h]);
           ++ground;
@@ -241,7 +268,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
           mbar_wait(&S.full[h], (ground >> 1) & 1);
-          x8_consume_round(s_ring + h * KX_PROD * X8_TILE, lane, j, P, sx, sy);
+          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, P, sx, sy);
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
@@ -272,41 +299,47 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
       if (!chainw) {
         // 7. project_pt + new-frame placement of this warp's patches (7m + warp), lanes = patches
         {
-          const int i = lane * KX_PROD + warp;
+          const int i = lane * NP + warp;
           int v = 0;
           if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4);
           const int nvw = __popc(__ballot_sync(0xffffffffu, v));
           if (lane == 0) s_nv[warp] = nvw;
         }
         __syncwarp();
-        // 8. one patch per round; the new-frame rows of the NEXT patch are fetched one round ahead
-        V8Rows ln = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool lvis = false;
-        auto fetch = [&](int i) {
-          const float4 pa = s_npl[2 * i];
-          lw = s_npl[2 * i + 1];
-          lvis = __float_as_int(pa.y) != 0;
-          if (lvis) ln = v8_load(Inew, __float_as_int(pa.x) + (2 * q2 - 1) * width + cc, width);
+        // 8. one patch per round; the new-frame rows of a patch are fetched TWO rounds ahead: a round is shorter than
+        // the L2 round trip of the gather (~900 cycles), so with one round of lead every producer stalled on its loads
+        // and the chain warp on the producers
+        struct Pre {
+          V8Rows ln;
+          float4 lw;
+          bool lvis;
         };
-        if (warp < P) fetch(warp);
+        auto fetch = [&](int i, Pre& o) {
+          const float4 pa = s_npl[2 * i];
+          o.lw = s_npl[2 * i + 1];
+          o.lvis = __float_as_int(pa.y) != 0;
+          if (o.lvis) o.ln = v8_load(Inew, __float_as_int(pa.x) + (2 * q2 - 1) * width + cc, width);
+        };
+        Pre cur = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, make_float4(0.f, 0.f, 0.f, 0.f), false}, nx1 = cur, nx2 = cur;
+        if (warp < P) fetch(warp, cur);
+        if (warp + NP < P) fetch(warp + NP, nx1);
         for (int j = 0; j < ROUNDS; ++j) {
-          const int i = j * KX_PROD + warp;
+          const int i = j * NP + warp;
           const int h = ground & 1, use = ground >> 1;
           const bool have = i < P;
           float v0[6], v1[6];
+          if (i + 2 * NP < P) fetch(i + 2 * NP, nx2);
           if (have) {
-            const bool vis = lvis;
+            const bool vis = cur.lvis;
             float2 pn = make_float2(0.f, 0.f);
             if (vis) {
-              pn = v8_bilin_exact(ln, lw);           // util_getPatch (utilities.cpp:55-113), unfused
+              pn = v8_bilin_exact(cur.ln, cur.lw);   // util_getPatch (utilities.cpp:55-113), unfused
               if (pnorm) {                           // utilities.cpp:111-112, Eigen's order
                 const float mn = x8_patch_sum(pn.x, pn.y) / N;
                 pn.x = pn.x - mn;
                 pn.y = pn.y - mn;
               }
             }
-            if (i + KX_PROD < P) fetch(i + KX_PROD);
             const float2 R = s_ref2[i * 32 + lane], GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
             float ab[12];
 #pragma unroll
@@ -319,18 +352,31 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
             for (int k = 0; k < 6; ++k) { v0[k] = sd0[k] * p0; v1[k] = sd1[k] * p1; }   // sd_k_proj, :386-391
           }
           if (use > 0) mbar_wait_relaxed(&S.empty[h], (use - 1) & 1);
-          if (have) x8_store(s_ring + (h * KX_PROD + warp) * X8_TILE, q2, cc, v0, v1);
+          if (have) x8_store(s_ring + (h * NP + warp) * X8_TILE, q2, cc, v0, v1);
           mbar_arrive(&S.full[h]);
           ++ground;
+          cur = nx1;
+          nx1 = nx2;
         }
       } else {
+        long long tc0 = 0, tw = 0, tcons = 0;   // instrumentation (trace only)
+        if (trace) tc0 = clock64();
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
-          mbar_wait(&S.full[h], (ground >> 1) & 1);
-          x8_consume_round(s_ring + h * KX_PROD * X8_TILE, lane, j, P, sx, sy);
+          if (trace && j == 0) {
+            const long long ta = clock64();
+            mbar_wait(&S.full[h], (ground >> 1) & 1);
+            tw = clock64() - ta;
+          } else {
+            mbar_wait(&S.full[h], (ground >> 1) & 1);
+          }
+          const long long tq = trace ? clock64() : 0;
+          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, P, sx, sy);
+          if (trace) tcons += clock64() - tq;
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
+        const long long tc1 = trace ? clock64() : 0;
         // 9a. sumsd[k]: Eigen's redux of the eight chains
         const float rx = kx_finish(sx), ry = kx_finish(sy);
         if ((lane & 7) == 0) {
@@ -340,7 +386,7 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
         __syncwarp();
         int nv = 0;
         if (lane == 0) {
-          for (int w = 0; w < KX_PROD; ++w) nv += s_nv[w];
+          for (int w = 0; w < NP; ++w) nv += s_nv[w];
           float sumsd[6], dp[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) sumsd[k] = S.sum[k];
@@ -364,6 +410,10 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
             rec[14] = normdp;
             rec[15] = (float)nv;
             for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+            rec[16] = (float)(tc1 - tc0);          // cycles of the chain loop ...
+            rec[17] = (float)tw;                   // ... of which waiting for the producers
+            rec[18] = (float)(clock64() - tc1);    // redux, solve, exp
+            rec[19] = (float)tcons;                // additions + loads of the chain warp alone
           }
         }
         __syncwarp();
@@ -401,37 +451,48 @@ __global__ void __launch_bounds__(256, 2) k_track_x8(const TrackParams prm) {
   }
 }
 
-size_t kx8_smem_bytes(const ict_optparam& op, int max_pts) {
+static size_t kx8_smem_np(const ict_optparam& op, int max_pts, int np) {
   const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
-  return sizeof(float) * (3 * 64 * P + 2 * KX_PROD * X8_TILE + 36 * P);
+  return sizeof(float) * (3 * 64 * P + 2 * np * X8_TILE + 36 * P);
 }
+size_t kx8_smem_bytes(const ict_optparam& op, int max_pts) { return kx8_smem_np(op, max_pts, KX_PROD); }
 
 bool kx8_supported(const ict_optparam& op, int max_pts) {
   const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
   return op.psz == 8 && P <= KX_PROD * X8_MAXR && kx8_smem_bytes(op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT;
 }
 
-template <bool PN>
+template <bool PN, int NP>
 static cudaError_t launch_x8_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
   static bool attr_dev[64] = {};            // function attributes are per device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_track_x8<PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x8<PN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(k_track_x8<PN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x8<PN, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_track_x8<PN><<<prm.T, 256, smem, stream>>>(prm);
+  k_track_x8<PN, NP><<<prm.T, (NP + 1) * 32, smem, stream>>>(prm);
   count_launch_external();
   return cudaGetLastError();
 }
 
 cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
-  const size_t smem = kx8_smem_bytes(prm.op, max_pts);
-  return prm.op.dopatchnorm ? launch_x8_t<true>(prm, smem, stream) : launch_x8_t<false>(prm, smem, stream);
+  const size_t smem7 = kx8_smem_np(prm.op, max_pts, 7), smem15 = kx8_smem_np(prm.op, max_pts, 15);
+  int sms = 148;
+  {
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
+  }
+  // 15 producers where they cost no residency: one CTA per SM anyway (more than 113 KB with 7), or a batch that does not
+  // fill the SMs twice
+  const bool wide = smem15 <= (size_t)ICT_TRACK_SMEM_LIMIT && (2 * (smem7 + 1024) > 228 * 1024 || prm.T <= sms);
+  if (wide) return prm.op.dopatchnorm ? launch_x8_t<true, 15>(prm, smem15, stream) : launch_x8_t<false, 15>(prm, smem15, stream);
+  return prm.op.dopatchnorm ? launch_x8_t<true, 7>(prm, smem7, stream) : launch_x8_t<false, 7>(prm, smem7, stream);
 }
 
 }  // namespace ict

@@ -648,3 +648,54 @@ def test_robustness_modes_against_ground_truth(ict):
     # the modes are not parity: the reference-order path refuses them
     with pytest.raises(IctError):
         run(sc, A, B, pts, npts, T, ROBUST_FULL_STEP, order=1)
+
+
+EXTREME = [
+    dict(psz=32, w=1280, h=704, npts=4, ntracks=10),     # K2r / K2v2
+    dict(psz=8, npts=60, ntracks=10),                    # K2x8 / K2v8
+    dict(psz=16, npts=9, ntracks=10),                    # general kernel / k_track_fast
+]
+
+
+@pytest.mark.parametrize("kw", EXTREME, ids=["psz32", "psz8", "psz16"])
+def test_extreme_poses_stay_in_bounds(ict, orc, kw):
+    """Poses that throw the patch centres far outside the padded planes, behind the camera or to infinity: the
+    visibility test (odometer.cpp:369-371) must keep every placement inside the planes.  compute-sanitizer is closed on
+    this pool, so the check is behavioural: reference order bit-identical to the oracle (an out-of-bounds read would
+    have to return the oracle's values), both orders deterministic across runs, well-formed outputs, and an ordinary
+    batch run right afterwards on the same device still bit-identical."""
+    case = make_case(seed=301, **kw)
+    T = case["T"]
+    p_in = np.zeros((T, 6))
+    p_in[0, 0] = 1e6                     # a million units sideways
+    p_in[1, 1] = -3e4
+    p_in[2, 2] = -50.0                   # behind the camera: negative depth
+    p_in[3, 2] = -1.0                    # through the camera plane (depth ~ 0 for part of the points)
+    p_in[4, 3] = np.pi                   # half a turn about x
+    p_in[5, 4] = 0.5 * np.pi             # quarter turn about y: depth ~ 0
+    p_in[6, 5] = 3.0                     # in-plane rotation: most points leave the frame
+    p_in[7, :3] = (1e20, -1e20, 1e20)    # float overflow in the projection
+    p_in[8, 2] = 1e6                     # a million units away: all points on the principal point
+    p_in[9, :] = (0.3, -0.2, 0.1, 0.2, -0.3, 0.1)
+    o = oracle_run(orc, case, trace_cap=48, p_in=p_in)
+    g1 = gpu_run(ict, case, trace_cap=48, sum_order=1, p_in=p_in)
+    assert_bit_identical(g1, o)
+    g1b = gpu_run(ict, case, trace_cap=48, sum_order=1, p_in=p_in)
+    assert np.array_equal(g1["p_out"], g1b["p_out"], equal_nan=True)
+    g0 = gpu_run(ict, case, trace_cap=48, sum_order=0, p_in=p_in)
+    g0b = gpu_run(ict, case, trace_cap=48, sum_order=0, p_in=p_in)
+    assert np.array_equal(g0["p_out"], g0b["p_out"], equal_nan=True) and np.array_equal(g0["iters"], g0b["iters"])
+    assert (g0["iters"] >= 0).all() and (g0["iters"] <= case["op"].maxiter).all()
+    assert (g0["npixres"] >= 0).all()
+    # a non-finite pose entry is undefined in the reference (it would index memory with it); here: no placement at all
+    p_bad = np.zeros((T, 6))
+    p_bad[0, 0] = np.nan
+    p_bad[1, 4] = np.inf
+    for order in (1, 0):
+        gb = gpu_run(ict, case, trace_cap=0, sum_order=order, p_in=p_bad)
+        assert gb["npixres"][0] == 0 and gb["npixres"][1] == 0
+        assert np.isfinite(gb["p_out"][2:]).all()
+    # the device is still sound: an ordinary run is bit-identical to the oracle
+    o2 = oracle_run(orc, case, trace_cap=48)
+    g2 = gpu_run(ict, case, trace_cap=48, sum_order=1)
+    assert_bit_identical(g2, o2)
