@@ -97,8 +97,7 @@ struct __align__(16) KrShared {
   unsigned long long gat_full[2];          // reference windows of a level landed: points 0..3 / points 4..7
   unsigned pd_flag[KR_MAXU];               // serial number of the iteration whose pdiff rows of the unit are written
   unsigned b_flag;                         // ... in which chain warp B has published its two sums
-  unsigned lu_flag;                        // serial number of the level whose LU factors are in f
-  unsigned pad_[2];
+  unsigned pad_[3];
   float G[12];
   float p[8];
   float sum[8];
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     mbar_init(&S.gat_full[0], 1);
     mbar_init(&S.gat_full[1], 1);
     S.b_flag = 0u;
-    S.lu_flag = 0u;
+
   }
   mbar_fence_init();
   __syncthreads();
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
       }
     };
 
-    // ---- 4a. per point: reference placement (odometer.cpp:268-279) ------------------------------------------------
+    // ---- 4a. per point: reference placement + steepest-descent coefficients (odometer.cpp:268-279, 306-326) ------
     if (tid < P) {
       const int i = tid;
       const float xc = S.Xc[i], yc = S.Yc[i], zc = S.Zc[i];
@@ -339,7 +338,14 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
       const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
       int x0 = 0, y0 = 0;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vis) kr_patch_place(mx, my, &x0, &y0, &w);
+      if (vis) {
+        kr_patch_place(mx, my, &x0, &y0, &w);
+        float c[10];
+        sd_coefs(xc, yc, zc, fx, fy, c);
+        float* ab = s_AB[i];
+        ab[0] = c[0]; ab[1] = 0.0f; ab[2] = c[2]; ab[3] = c[4]; ab[4] = c[6]; ab[5] = c[8];
+        ab[6] = 0.0f; ab[7] = c[1]; ab[8] = c[3]; ab[9] = c[5]; ab[10] = c[7]; ab[11] = c[9];
+      }
       S.rpl[i] = w;
       S.rx[i] = x0;
       S.ry[i] = y0;
@@ -364,15 +370,6 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
       }
       __syncwarp();
       if (lane < 2) mbar_arrive(&S.gat_full[lane]);
-      // 4a'. steepest-descent coefficients of the points (odometer.cpp:306-326; double-promoted terms, ~2000 cycles)
-      // while the boxes are in flight: first needed by the sd store, two CTA barriers further down
-      if (lane < P && S.rvis[lane]) {
-        float c[10];
-        sd_coefs(S.Xc[lane], S.Yc[lane], S.Zc[lane], fx, fy, c);
-        float* ab = s_AB[lane];
-        ab[0] = c[0]; ab[1] = 0.0f; ab[2] = c[2]; ab[3] = c[4]; ab[4] = c[6]; ab[5] = c[8];
-        ab[6] = 0.0f; ab[7] = c[1]; ab[8] = c[3]; ab[9] = c[5]; ab[10] = c[7]; ab[11] = c[9];
-      }
     }
     if (chainA && trace) lt1 = clock64();
     // ---- 4c/5. template gather (util_getPatch_grad, utilities.cpp:115-189) and steepest-descent values ------------
@@ -477,11 +474,11 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     }
     fence_proxy_async();   // the sd coefficients in slot 0, before the first window lands there
     __syncthreads();
-    // ---- first placement; the factorisation (Hes.fullPivLu(), odometer.cpp:514; once per level: the matrix does not
-    // change) runs on the last producer warp underneath the first iteration's chains — its result is first needed by
-    // that iteration's solve, and its units (the last of each round) are the last the chain warps get to
+    // ---- factorisation (Hes.fullPivLu(), odometer.cpp:514; once per level: the matrix does not change) -------------
     if (chainA && trace) lt3 = clock64();
     if (chainA) {
+      lu6_factor_warp(S.Hsum, S.f);
+
       normdp_init = 1e-10f;              // odometer.cpp:341-342
       const int cont0 = (0 < op.maxiter) & ((1e-10f / 1e-10f) > op.normdp_ratio);
       if (lane == 0) {
@@ -498,11 +495,6 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
     while (S.cont[gi & 1u]) {
       const unsigned par = gi & 1u;
       if (prod) {
-        if (it == 0 && pw == NPROD - 1) {
-          lu6_factor_warp(S.Hsum, S.f);
-          __syncwarp();
-          if (lane == 0) st_release_s(&S.lu_flag, lvl + 1u);
-        }
         // 8. new-frame patches + residual (util_getPatch utilities.cpp:55-113, odometer.cpp:381), in place in the window
 #pragma unroll
         for (int s = 0; s < UPP; ++s) {
@@ -565,7 +557,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
         const int k = chainA ? (lane >> 3) : 4 + ((lane >> 3) & 1);
         const float4* sdk = reinterpret_cast<const float4*>(s_sd) + k * 256 + c;
         float acc = -0.0f;   // -0 + x == x for every x: the chain starts with its first element (Eigen's redux)
-        long long t_c0 = 0, t_c1 = 0, w0 = 0, w_units = 0, t_u0 = 0;   // instrumentation (chain warp A, trace only)
+        long long t_c0 = 0, t_c1 = 0, w0 = 0;   // instrumentation (chain warp A, trace only)
         const unsigned want = gi + 1u;
         if (chainA && trace) t_c0 = clock64();
         while (ld_acquire_s(&S.pd_flag[0]) != want) {}
@@ -594,15 +586,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.slot_free[u]);
-          if (chainA && trace) {
-            const long long tw = clock64();
-            while (nf != want) nf = ld_acquire_s(&S.pd_flag[u + 1]);
-            const long long te = clock64();
-            w_units += te - tw;
-            if (u == 0) t_u0 = tw - (t_c0 + w0);
-          } else {
-            while (nf != want) nf = ld_acquire_s(&S.pd_flag[u + 1]);
-          }
+          while (nf != want) nf = ld_acquire_s(&S.pd_flag[u + 1]);
         }
         const float res = kx_finish(acc);   // Eigen's redux of the eight chains
         if (!chainA) {
@@ -611,8 +595,6 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
           if (lane == 0) st_release_s(&S.b_flag, want);
         } else {
           if ((lane & 7) == 0) S.sum[lane >> 3] = res;
-          if (it == 0)
-            while (ld_acquire_s(&S.lu_flag) != lvl + 1u) {}
           float lu[36];                   // the level's LU factors (column-major), every lane alike
 #pragma unroll
           for (int j = 0; j < 36; ++j) lu[j] = S.f.lu[j];
@@ -652,11 +634,7 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
               for (int j = 16; j < ICT_TRACE_FLOATS; ++j) rec[j] = 0.0f;
               rec[16] = (float)w0;
               rec[17] = (float)(t_s1 - t_c1);        // redux hand-off + solve
-              if (it != 0) {
-                rec[18] = (float)(t_s2 - t_s1);   // pose update + exp
-                rec[19] = (float)w_units;         // chain loop: cycles spent waiting for units 1.. to be produced
-                rec[20] = (float)t_u0;            // chain loop: cycles of the first unit's loads and additions
-              }
+              if (it != 0) rec[18] = (float)(t_s2 - t_s1);   // pose update + exp
               if (it == 0) {   // first record of a level: cycles of its precompute phases
                 rec[19] = (float)(lt1 - lt0);   // acquires, reference placement, window issue
                 rec[20] = (float)(lt2 - lt1);   // window wait, sampling, sd store

@@ -21,8 +21,6 @@ for k in (16,):
     v = tr[..., k][ok]
     if v.any():
         print("field %d: mean %.0f median %.0f" % (k, v.mean(), np.median(v)))
-print("chain loop, iterations > 0: waiting for units 1..: mean %.0f   first unit (16 rows) loads + additions: mean %.0f median %.0f" %
-      (tr[..., 19][later].mean(), tr[..., 20][later].mean(), np.median(tr[..., 20][later])))
 first = ok & (tr[..., 1] == 0)
 for k, name in ((19, "level: acquires + ref placement + window issue"), (20, "level: window wait + sampling + sd store"),
                 (21, "level: Hessian"), (18, "level: factorisation + first placement")):
