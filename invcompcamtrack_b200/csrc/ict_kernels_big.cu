@@ -44,6 +44,11 @@ static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #define BIG_CHUNK 512          /* chain elements per staged chunk (2 KB) of the reference-order chain kernel */
 #define BIG_STAGES 4
+// position of element j of chain c of product row q: chunk-major — the eight chains' 512-element pieces of one chunk
+// are contiguous (16 KB), so that a stage of the chain kernel is ONE bulk copy
+__host__ __device__ __forceinline__ long long big_prod_idx(int q, int c, long long j, long long cstride) {
+  return (long long)q * 8 * cstride + ((j / BIG_CHUNK) * 8 + c) * BIG_CHUNK + (j % BIG_CHUNK);
+}
 static long long big_cstride(int64_t Nfull) {
   const long long nj = (Nfull + 7) / 8;
   return ((nj + BIG_CHUNK - 1) / BIG_CHUNK) * BIG_CHUNK;
@@ -66,7 +71,7 @@ size_t bigtrack_work_bytes(const ict_optparam& op, int64_t npts) {
   b += al(sizeof(float) * 10 * P) + al(sizeof(float) * 4 * P) + 4 * al(sizeof(float) * P);
   b += 2 * al(sizeof(int) * P);
   b += al(sizeof(float) * 21 * big_ncta(E));
-  b += al(sizeof(float) * 48 * (size_t)big_cstride((int64_t)op.maxpttrack * op.novals));
+  b += al(sizeof(float) * 8 * 24 * (size_t)big_cstride((int64_t)op.maxpttrack * op.novals));   // 24 product rows: the 21 Hessian sums at once
   return b;
 }
 
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(256) k_big_products(const BigArgs a, int pass)
           }
         }
 #pragma unroll
-        for (int q = 0; q < 6; ++q) a.w.prod[(q * 8 + c) * a.w.cstride + j] = v[q];
+        for (int q = 0; q < 6; ++q) a.w.prod[big_prod_idx((MODE == 1 ? 6 * pass : 0) + q, c, j, a.w.cstride)] = v[q];
       }
     }
   }
@@ -482,12 +487,12 @@ __global__ void __launch_bounds__(256) k_big_products(const BigArgs a, int pass)
 
 // One CTA (one warp) per quantity q < nq.  out[q] = the Eigen-order sum of the quantity's E values (zeros up to
 // Nfull), finished like redux_impl::run with the few tail elements re-read from the product rows.
-__global__ void __launch_bounds__(32) k_big_chains(const BigArgs a, int nq, float* out, int iteration) {
+__global__ void __launch_bounds__(64) k_big_chains(const BigArgs a, int nq, float* out, int iteration) {
   if (iteration && !a.w.st->cont) return;
   extern __shared__ __align__(128) float s_ring[];     // [BIG_STAGES][8][BIG_CHUNK]
-  __shared__ unsigned long long s_full[BIG_STAGES];
+  __shared__ unsigned long long s_full[BIG_STAGES], s_free[BIG_STAGES];
   __shared__ float s_ch[8];
-  const int q = blockIdx.x, lane = threadIdx.x;
+  const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (q >= nq) return;
   const int Nfull = a.prm.op.maxpttrack * a.prm.op.novals, E = (int)a.E;
   const int as2 = (Nfull / 8) * 8, lim = as2 < E ? as2 : E;
@@ -495,19 +500,24 @@ __global__ void __launch_bounds__(32) k_big_chains(const BigArgs a, int nq, floa
   // chain c has cnt_c = #{e < lim : e % 8 == c} elements; all chains need ceil(lim / 8) positions at most
   const int njmax = (lim + 7) / 8;
   const int nchunk = (njmax + BIG_CHUNK - 1) / BIG_CHUNK;
-  if (lane < BIG_STAGES) mbar_init(&s_full[lane], 1);
+  if (threadIdx.x < BIG_STAGES) {
+    mbar_init(&s_full[threadIdx.x], 1);
+    mbar_init(&s_free[threadIdx.x], 1);
+  }
   mbar_fence_init();
-  __syncwarp();
-  auto issue = [&](int chunk) {     // lane 0: the eight rows' chunk into stage chunk % BIG_STAGES
-    const int st = chunk % BIG_STAGES;
-    mbar_expect_tx(&s_full[st], 8u * BIG_CHUNK * sizeof(float));
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      bulk_g2s(s_ring + (st * 8 + c) * BIG_CHUNK, rows + c * a.w.cstride + (long long)chunk * BIG_CHUNK, BIG_CHUNK * sizeof(float),
-               &s_full[st]);
-  };
-  if (lane == 0)
-    for (int k = 0; k < BIG_STAGES && k < nchunk; ++k) issue(k);
+  __syncthreads();
+  if (warp == 1) {
+    // the copy warp: a chunk's eight rows (contiguous, 16 KB) into stage chunk % BIG_STAGES as soon as the chain warp
+    // has released the stage — kept off the chain warp, whose every cycle is on the critical path
+    if (lane == 0)
+      for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int st = chunk % BIG_STAGES, use = chunk / BIG_STAGES;
+        if (use > 0) mbar_wait(&s_free[st], (use - 1) & 1);
+        mbar_expect_tx(&s_full[st], 8u * BIG_CHUNK * sizeof(float));
+        bulk_g2s(s_ring + st * 8 * BIG_CHUNK, rows + (long long)chunk * 8 * BIG_CHUNK, 8u * BIG_CHUNK * sizeof(float), &s_full[st]);
+      }
+    return;
+  }
   const int c = lane & 7;
   const int cnt = c < lim ? (lim - c + 7) / 8 : 0;      // this chain's elements
   float acc = -0.0f;                                     // -0 + x == x: the chain starts with its first element
@@ -518,23 +528,33 @@ __global__ void __launch_bounds__(32) k_big_chains(const BigArgs a, int nq, floa
       const float4* p4 = reinterpret_cast<const float4*>(s_ring + (st * 8 + c) * BIG_CHUNK);
       const int have = min(BIG_CHUNK, cnt - chunk * BIG_CHUNK);     // may be <= 0 for the last chunk of a short chain
       int i = 0;
-      for (; i + 16 <= have; i += 16) {
-        const float4 v0 = p4[i / 4], v1 = p4[i / 4 + 1], v2 = p4[i / 4 + 2], v3 = p4[i / 4 + 3];
-        acc = acc + v0.x; acc = acc + v0.y; acc = acc + v0.z; acc = acc + v0.w;
-        acc = acc + v1.x; acc = acc + v1.y; acc = acc + v1.z; acc = acc + v1.w;
-        acc = acc + v2.x; acc = acc + v2.y; acc = acc + v2.z; acc = acc + v2.w;
-        acc = acc + v3.x; acc = acc + v3.y; acc = acc + v3.z; acc = acc + v3.w;
+      if (have >= 32) {
+        // 32 elements per trip, the next trip's eight quads loaded ahead of this trip's 32 dependent additions
+        float4 v[8], n[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = p4[r];
+        for (; i + 64 <= have; i += 32) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) n[r] = p4[i / 4 + 8 + r];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { acc = acc + v[r].x; acc = acc + v[r].y; acc = acc + v[r].z; acc = acc + v[r].w; }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) v[r] = n[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { acc = acc + v[r].x; acc = acc + v[r].y; acc = acc + v[r].z; acc = acc + v[r].w; }
+        i += 32;
       }
       const float* p1 = reinterpret_cast<const float*>(p4);
       for (; i < have; ++i) acc = acc + p1[i];
     }
-    __syncwarp();                                        // every chain lane has read the stage: refill it
-    if (lane == 0 && chunk + BIG_STAGES < nchunk) issue(chunk + BIG_STAGES);
+    __syncwarp();                                        // every chain lane has read the stage: hand it back
+    if (lane == 0) mbar_arrive(&s_free[st]);
   }
   if (lane < 8) s_ch[lane] = cnt > 0 ? acc : 0.0f;
   __syncwarp();
   if (lane == 0) {
-    auto val = [&](int e) { return rows[(e & 7) * a.w.cstride + (e >> 3)]; };
+    auto val = [&](int e) { return a.w.prod[big_prod_idx(q, e & 7, e >> 3, a.w.cstride)]; };
     out[q] = eigen_finish(s_ch, val, Nfull, E);
   }
 }
@@ -928,7 +948,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const bool ex = prm.sum_mode != 0;   // reference-order sums
   const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !ict_knob("ICT_DENSE_V1");
   int nl = 0;
-  const size_t chain_smem = sizeof(float) * BIG_STAGES * 8 * BIG_CHUNK;    // 64 KB
+  const size_t chain_smem = sizeof(float) * BIG_STAGES * 8 * BIG_CHUNK;    // 65 KB
   if (ex) {
     static bool attr_dev[64] = {};            // function attributes are per device
     int dev_ = 0;
@@ -983,10 +1003,10 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
     k_big_level_gather<<<ncta, 256, 0, st>>>(a, sl); ++nl;
     if (pn) { k_big_patch_means<<<pcta, 256, 0, st>>>(a, a.w.ref, 1, 1, ex ? 1 : 0); ++nl; }
     if (ex) {
-      for (int pass = 0; pass < 4; ++pass) {      // 21 sums, six product rows at a time
-        k_big_products<1><<<ncta, 256, 0, st>>>(a, pass); ++nl;
-        k_big_chains<<<pass < 3 ? 6 : 3, 32, chain_smem, st>>>(a, pass < 3 ? 6 : 3, a.w.part + 6 * pass, 0); ++nl;
-      }
+      // the products of all 21 sums (four passes of six rows), then their 21 x 8 chains side by side: one chain pass
+      // (E / 8 dependent additions) per level instead of four
+      for (int pass = 0; pass < 4; ++pass) { k_big_products<1><<<ncta, 256, 0, st>>>(a, pass); ++nl; }
+      k_big_chains<<<21, 64, chain_smem, st>>>(a, 21, a.w.part, 0); ++nl;
       k_big_hessian_exact_finish<<<1, 32, 0, st>>>(a); ++nl;
     } else {
       k_big_level_hessian<<<ncta, 256, 0, st>>>(a); ++nl;
@@ -1002,7 +1022,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
         if (pn) k_big_iter_pdiff<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_pdiff<false><<<ncta, 256, 0, st>>>(a, sl);
         ++nl;
         k_big_products<0><<<ncta, 256, 0, st>>>(a, 0); ++nl;
-        k_big_chains<<<6, 32, chain_smem, st>>>(a, 6, a.w.part, 1); ++nl;
+        k_big_chains<<<6, 64, chain_smem, st>>>(a, 6, a.w.part, 1); ++nl;
       } else {
         if (pn) k_big_iter_elems<true><<<ncta, 256, 0, st>>>(a, sl); else k_big_iter_elems<false><<<ncta, 256, 0, st>>>(a, sl);
         ++nl;
