@@ -40,6 +40,39 @@ __global__ void k(float* out, long long* cyc, int mode) {
         }
       }
     }
+  } else if (mode == 7 || mode == 8 || mode == 9) {
+    // mode 0 plus the per-unit hand-offs of the kernel: 7 = __syncwarp + mbarrier.arrive by lane 0; 8 = + ld.acquire peek;
+    // 9 = only the ld.acquire peek
+    __shared__ unsigned long long bar[8];
+    __shared__ unsigned flag[8];
+    if (threadIdx.x < 8) { flag[threadIdx.x] = 1u;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar[threadIdx.x])), "r"(1 << 19)); }
+    __syncthreads();
+    t0 = clock64();
+#pragma unroll 1
+    for (int u = 0; u < REP; ++u) {
+      const float4* sd4 = sdk + ((u >> 1) & 3) * 1536 + (u & 1) * 128;
+      const float4* pd4 = pdb + (u & 1) * 320;
+      unsigned nf = 1u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 d[8], a[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { d[r] = pd4[(8 * h + r) * 10]; a[r] = sd4[(8 * h + r) * 8]; }
+        if (h == 1 && mode >= 8)
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(nf) : "r"((unsigned)__cvta_generic_to_shared(&flag[(u + 1) & 7])) : "memory");
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          acc = acc + a[r].x * d[r].x; acc = acc + a[r].y * d[r].y; acc = acc + a[r].z * d[r].z; acc = acc + a[r].w * d[r].w;
+        }
+      }
+      if (mode <= 8) {
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&bar[u & 7])) : "memory");
+      }
+      while (nf != 1u)
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(nf) : "r"((unsigned)__cvta_generic_to_shared(&flag[(u + 1) & 7])) : "memory");
+    }
   } else if (mode == 1) {
     // two rows ahead
     const float4* sd4 = sdk; const float4* pd4 = pdb;
@@ -153,7 +186,7 @@ int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 4 * 1024 * 64); cudaMallocManaged(&cyc, 64);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000);
-  for (int mode = 0; mode < 7; ++mode)
+  for (int mode = 0; mode < 10; ++mode)
     for (int nw = 1; nw <= 8; nw *= 2) {
       k<<<1, 32 * nw, 116000>>>(out, cyc, mode); cudaDeviceSynchronize();
       printf("mode %d warps %d: %6.1f cycles per row\n", mode, nw, (double)cyc[0] / REP / 16);
