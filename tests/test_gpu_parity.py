@@ -699,3 +699,21 @@ def test_extreme_poses_stay_in_bounds(ict, orc, kw):
     o2 = oracle_run(orc, case, trace_cap=48)
     g2 = gpu_run(ict, case, trace_cap=48, sum_order=1)
     assert_bit_identical(g2, o2)
+
+
+@pytest.mark.parametrize("kw", [dict(npts=24, ntracks=170), dict(npts=24, ntracks=170, dopatchnorm=1, donorm=1),
+                                dict(npts=110, ntracks=150)])
+def test_psz8_reference_order_both_launch_forms(ict, orc, kw):
+    """K2x8 runs with seven producer warps (two CTAs per SM) for batches larger than the SM count of tracks up to 100
+    points, with fifteen otherwise (small batches, tracks beyond 100 points): both bit-identical to the oracle, and a
+    track's result independent of which form its batch took."""
+    case = make_case(seed=311, psz=8, **kw)
+    o = oracle_run(orc, case, trace_cap=48)
+    g = gpu_run(ict, case, trace_cap=48, sum_order=1)
+    assert_bit_identical(g, o)
+    sub = dict(case)
+    sub["T"] = 9
+    sub["pt_off"] = case["pt_off"][:10]
+    sub["pts"] = case["pts"][:3 * int(case["pt_off"][9])]      # per track: X block, Y block, Z block
+    gs = gpu_run(ict, sub, trace_cap=48, sum_order=1)
+    assert np.array_equal(gs["p_out"], g["p_out"][:9]) and np.array_equal(gs["iters"], g["iters"][:9])
