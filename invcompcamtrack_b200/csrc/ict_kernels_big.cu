@@ -42,8 +42,10 @@ struct BigWork {
 
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
-#define BIG_CHUNK 512          /* chain elements per staged chunk (2 KB) of the reference-order chain kernel */
-#define BIG_STAGES 4
+#define BIG_CHUNK 2048         /* chain elements per staged chunk (8 KB per chain, 64 KB per stage) of the reference-order
+                                  chain kernel: every chunk costs ~150 cycles of hand-over on the critical path, so few and
+                                  large ones (512 x 4 stages: 0.66 ms per pass of 247 k additions; 2048 x 2: 0.585 ms) */
+#define BIG_STAGES 2
 // position of element j of chain c of product row q: chunk-major — the eight chains' 512-element pieces of one chunk
 // are contiguous (16 KB), so that a stage of the chain kernel is ONE bulk copy
 __host__ __device__ __forceinline__ long long big_prod_idx(int q, int c, long long j, long long cstride) {
@@ -432,8 +434,8 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
 //   1. k_big_products (all SMs, streaming): the values to be summed — sd_k * pdiff for the six J^T r sums, sd_a * sd_b
 //      for six of the 21 Hessian sums per pass — with the reference's roundings, written CHAIN-MAJOR (the elements of
 //      chain c of quantity q contiguous), so that
-//   2. k_big_chains (one warp per quantity, lane c = chain c) streams its eight rows through a four-stage
-//      shared-memory ring with bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts, 2 KB per chain
+//   2. k_big_chains (one warp per quantity, lane c = chain c) streams its eight rows through a two-stage
+//      shared-memory ring with bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts, 8 KB per chain
 //      and stage) and does nothing but LDS.128 + four dependent additions per four elements.
 // Same additions in the same order as eigen_chain: the sums are bit-identical to the one-thread form (tested against
 // the oracle on dense alignment and on tracks of 700-900 8x8 patches).
@@ -948,7 +950,7 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
   const bool ex = prm.sum_mode != 0;   // reference-order sums
   const bool fused = !pn && !ex && !prm.force_general && op.novals == 1 && !ict_knob("ICT_DENSE_V1");
   int nl = 0;
-  const size_t chain_smem = sizeof(float) * BIG_STAGES * 8 * BIG_CHUNK;    // 65 KB
+  const size_t chain_smem = sizeof(float) * BIG_STAGES * 8 * BIG_CHUNK;    // 128 KB
   if (ex) {
     static bool attr_dev[64] = {};            // function attributes are per device
     int dev_ = 0;
