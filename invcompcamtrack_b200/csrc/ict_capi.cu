@@ -677,7 +677,7 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
     return fail(ICT_ERR_UNSUPPORTED, "robustness modes need the fast mode (sum order 0), psz 8 and at most 240 points per track");
   if (tr->keep_state) {
     // carried template state: implemented by the reference-order kernel for 8x8 patches (the drivers' configuration)
-    if (!(tr->sum_mode == 1 && !tr->force_general && kx8_supported(tr->op, tr->max_pts)))
+    if (!(tr->sum_mode == 1 && !tr->force_general && tr->op.psz == 8 && kx8_supported(tr->op, tr->max_pts)))
       return fail(ICT_ERR_UNSUPPORTED, "keep_state needs the reference summation order, psz 8 and at most 224 points per track");
     const int P = tr->max_pts < tr->op.maxpttrack ? tr->max_pts : tr->op.maxpttrack;
     prm.state_stride = (int64_t)(3 * 64 + 12) * P;

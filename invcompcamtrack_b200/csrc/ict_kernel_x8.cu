@@ -99,13 +99,49 @@ __device__ __forceinline__ void x8_store(float* tile, int q, int c, const float*
     *reinterpret_cast<float2*>(tile + (k * 8 + c) * 8 + ((2 * q) ^ (c & 4))) = make_float2(v0[k], v1[k]);
 }
 
+// The lane's texels for its two pixels of a tile.  TPP = tiles per point: 1 for 8x8 patches (a tile = the patch, lane
+// (q, c) = rows 2q, 2q + 1 of column c: three texel rows, shared middle one), 4 for 16x16 patches (tile tt = rows 4 tt ..
+// 4 tt + 3; with e = row * 16 + col chain c adds (row, c), (row, c + 8) row after row, so lane (q, c) = columns c and
+// c + 8 of row 4 tt + q: two texel rows, two column pairs).  Pixel (r, x) of a patch reads the texels at
+// base + r * width + x, - 1, - width, - width - 1 (bilin4).
+template <int TPP>
+struct XRows {
+  float v[TPP == 1 ? 6 : 8];
+};
+template <int TPP>
+__device__ __forceinline__ XRows<TPP> x_load(const float* __restrict__ pl, int base, int tt, int q, int c, int width) {
+  XRows<TPP> r;
+  if (TPP == 1) {
+    const int o = base + (2 * q - 1) * width + c;
+    r.v[0] = __ldg(pl + o);             r.v[1] = __ldg(pl + o - 1);
+    r.v[2] = __ldg(pl + o + width);     r.v[3] = __ldg(pl + o + width - 1);
+    r.v[4] = __ldg(pl + o + 2 * width); r.v[5] = __ldg(pl + o + 2 * width - 1);
+  } else {
+    const int o = base + (4 * tt + q - 1) * width + c;
+    r.v[0] = __ldg(pl + o);             r.v[1] = __ldg(pl + o - 1);
+    r.v[2] = __ldg(pl + o + width);     r.v[3] = __ldg(pl + o + width - 1);
+    r.v[4] = __ldg(pl + o + 8);         r.v[5] = __ldg(pl + o + 7);
+    r.v[6] = __ldg(pl + o + width + 8); r.v[7] = __ldg(pl + o + width + 7);
+  }
+  return r;
+}
+// util_getPatch / util_getPatch_grad (utilities.cpp:107, 181-183), unfused, reference order: the lane's two pixels
+template <int TPP>
+__device__ __forceinline__ float2 x_bilin(const XRows<TPP>& r, const float4 w) {
+  float2 v;
+  v.x = ((w.x * r.v[2] + w.y * r.v[3]) + w.z * r.v[0]) + w.w * r.v[1];
+  if (TPP == 1) v.y = ((w.x * r.v[4] + w.y * r.v[5]) + w.z * r.v[2]) + w.w * r.v[3];
+  else v.y = ((w.x * r.v[6] + w.y * r.v[7]) + w.z * r.v[4]) + w.w * r.v[5];
+  return v;
+}
+
 // NP producer warps + the chain warp.  NP = 7: 256 threads, two CTAs per SM up to 100 points per track (throughput form).
 // NP = 15: 512 threads, one CTA per SM — a producer's round is ~150 dependent unfused instructions (~900 cycles), so
 // the time of an iteration is rounds x 900 and twice the producers halve it; chosen when only one CTA fits an SM anyway
 // or when the batch is too small to fill the GPU twice (the reference's own use: one track per call).
-template <bool PN, int NP>
+template <bool PN, int NP, int TPP>
 __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(const TrackParams prm) {
-  constexpr int N = 64;
+  constexpr int N = 64 * TPP;          // pixels per patch
   extern __shared__ __align__(16) float smem[];
   __shared__ KxShared S;
   __shared__ int s_nv[NP + 1];
@@ -119,12 +155,13 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
   const bool donorm = op.donorm != 0;
   const bool pnorm = PN && op.dopatchnorm != 0;
   const int q2 = lane >> 3, cc = lane & 7;
-  const int ROUNDS = (P + NP - 1) / NP;
+  const int Q = P * TPP;                  // tiles of the track: 64 pixel-values of every sum each
+  const int ROUNDS = (Q + NP - 1) / NP;
 
-  float2* s_ref2 = reinterpret_cast<float2*>(smem);    // [P][32]: (row 2q, row 2q+1) of column c, lane = 8q + c
-  float2* s_gx2 = s_ref2 + 32 * P;
-  float2* s_gy2 = s_gx2 + 32 * P;
-  float* s_ring = reinterpret_cast<float*>(s_gy2 + 32 * P);   // [2][NP][X8_TILE]
+  float2* s_ref2 = reinterpret_cast<float2*>(smem);    // [Q][32]: the lane's two pixels of the tile (XRows), lane = 8q + c
+  float2* s_gx2 = s_ref2 + 32 * Q;
+  float2* s_gy2 = s_gx2 + 32 * Q;
+  float* s_ring = reinterpret_cast<float*>(s_gy2 + 32 * Q);   // [2][NP][X8_TILE]
   float4* s_rpl = reinterpret_cast<float4*>(s_ring + 2 * NP * X8_TILE);   // [P][2] reference placement
   float4* s_npl = s_rpl + 2 * P;                        // [P][2] new-frame placement
   float* s_AB = reinterpret_cast<float*>(s_npl + 2 * P);    // [P][12]
@@ -152,7 +189,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
     const float2 z2 = make_float2(0.f, 0.f);
     const float2* st2 = reinterpret_cast<const float2*>(state);
     const bool load = state && prm.state_load;
-    for (int e = tid; e < 3 * 32 * P; e += nt) s_ref2[e] = load ? st2[e] : z2;
+    for (int e = tid; e < 3 * 32 * Q; e += nt) s_ref2[e] = load ? st2[e] : z2;
     const float* q = prm.pt3d + 3 * off;
     for (int i = tid; i < P; i += nt) {
       s_X[i] = q[i];
@@ -206,7 +243,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
       const int vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
       PatchPlace pl = {0, 0.f, 0.f, 0.f, 0.f};
       if (vis) {
-        pl = patch_place(mx, my, 4, width);
+        pl = patch_place(mx, my, 4 * (TPP == 1 ? 1 : 2), width);
         float c[10];
         sd_coefs(xc, yc, zc, fx, fy, c);
         float* ab = s_AB + i * 12;
@@ -218,20 +255,22 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
     }
     __syncthreads();
     // ---- 4b. template gather (all eight warps; util_getPatch_grad, unfused, reference order) ------------------------
-    for (int i = warp; i < P; i += NP + 1) {
-      const float4 pa = s_rpl[2 * i], pw = s_rpl[2 * i + 1];
+    for (int i = warp; i < Q; i += NP + 1) {
+      const int ip = i / TPP, tt = i % TPP;
+      const float4 pa = s_rpl[2 * ip], pw = s_rpl[2 * ip + 1];
       if (__float_as_int(pa.y)) {
-        const int o = __float_as_int(pa.x) + (2 * q2 - 1) * width + cc;
-        const V8Rows ri = v8_load(Iref, o, width), rx = v8_load(Dxr, o, width), ry = v8_load(Dyr, o, width);
-        float2 r = v8_bilin_exact(ri, pw);
+        const int o = __float_as_int(pa.x);
+        const XRows<TPP> ri = x_load<TPP>(Iref, o, tt, q2, cc, width), rx = x_load<TPP>(Dxr, o, tt, q2, cc, width),
+                         ry = x_load<TPP>(Dyr, o, tt, q2, cc, width);
+        float2 r = x_bilin<TPP>(ri, pw);
         if (pnorm) {                     // utilities.cpp:187-188: tmp.sum() / novals, Eigen's order
           const float m = x8_patch_sum(r.x, r.y) / N;
           r.x = r.x - m;
           r.y = r.y - m;
         }
         s_ref2[i * 32 + lane] = r;
-        s_gx2[i * 32 + lane] = v8_bilin_exact(rx, pw);
-        s_gy2[i * 32 + lane] = v8_bilin_exact(ry, pw);
+        s_gx2[i * 32 + lane] = x_bilin<TPP>(rx, pw);
+        s_gy2[i * 32 + lane] = x_bilin<TPP>(ry, pw);
       }
     }
     __syncthreads();
@@ -244,11 +283,11 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
           const int h = ground & 1, use = ground >> 1;
           if (use > 0) mbar_wait_relaxed(&S.empty[h], (use - 1) & 1);
           const int i = j * NP + warp;
-          if (i < P) {
+          if (i < Q) {
             const float2 GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
             float ab[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
+            for (int k = 0; k < 12; ++k) ab[k] = s_AB[(i / TPP) * 12 + k];
             float sd0[6], sd1[6], v0[6], v1[6];
             kx_sd(GX.x, GY.x, ab, sd0);
             kx_sd(GX.y, GY.y, ab, sd1);
@@ -268,7 +307,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
         for (int j = 0; j < ROUNDS; ++j) {
           const int h = ground & 1;
           mbar_wait(&S.full[h], (ground >> 1) & 1);
-          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, P, sx, sy);
+          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, Q, sx, sy);
           mbar_arrive(&S.empty[h]);
           ++ground;
         }
@@ -301,39 +340,48 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
         {
           const int i = lane * NP + warp;
           int v = 0;
-          if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4);
+          if (i < P) v = place_point(S.G, s_X[i], s_Y[i], s_Z[i], fx, fy, cx, cy, swo, sho, width, s_npl + 2 * i, 4 * (TPP == 1 ? 1 : 2));
           const int nvw = __popc(__ballot_sync(0xffffffffu, v));
           if (lane == 0) s_nv[warp] = nvw;
         }
         __syncwarp();
+        // with several tiles per patch a warp's tiles belong to points placed by other producer warps
+        if (TPP > 1) asm volatile("bar.sync 2, %0;" ::"n"(NP * 32) : "memory");
         // 8. one patch per round; the new-frame rows of a patch are fetched TWO rounds ahead: a round is shorter than
         // the L2 round trip of the gather (~900 cycles), so with one round of lead every producer stalled on its loads
         // and the chain warp on the producers
         struct Pre {
-          V8Rows ln;
+          XRows<TPP> ln;
           float4 lw;
           bool lvis;
         };
         auto fetch = [&](int i, Pre& o) {
-          const float4 pa = s_npl[2 * i];
-          o.lw = s_npl[2 * i + 1];
+          const int ip = i / TPP;
+          const float4 pa = s_npl[2 * ip];
+          o.lw = s_npl[2 * ip + 1];
           o.lvis = __float_as_int(pa.y) != 0;
-          if (o.lvis) o.ln = v8_load(Inew, __float_as_int(pa.x) + (2 * q2 - 1) * width + cc, width);
+          if (o.lvis) o.ln = x_load<TPP>(Inew, __float_as_int(pa.x), i % TPP, q2, cc, width);
         };
-        Pre cur = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, make_float4(0.f, 0.f, 0.f, 0.f), false}, nx1 = cur, nx2 = cur;
-        if (warp < P) fetch(warp, cur);
-        if (warp + NP < P) fetch(warp + NP, nx1);
+        Pre cur, nx1, nx2;
+#pragma unroll
+        for (int k = 0; k < (TPP == 1 ? 6 : 8); ++k) cur.ln.v[k] = 0.0f;
+        cur.lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        cur.lvis = false;
+        nx1 = cur;
+        nx2 = cur;
+        if (warp < Q) fetch(warp, cur);
+        if (warp + NP < Q) fetch(warp + NP, nx1);
         for (int j = 0; j < ROUNDS; ++j) {
           const int i = j * NP + warp;
           const int h = ground & 1, use = ground >> 1;
-          const bool have = i < P;
+          const bool have = i < Q;
           float v0[6], v1[6];
-          if (i + 2 * NP < P) fetch(i + 2 * NP, nx2);
+          if (i + 2 * NP < Q) fetch(i + 2 * NP, nx2);
           if (have) {
             const bool vis = cur.lvis;
             float2 pn = make_float2(0.f, 0.f);
             if (vis) {
-              pn = v8_bilin_exact(cur.ln, cur.lw);   // util_getPatch (utilities.cpp:55-113), unfused
+              pn = x_bilin<TPP>(cur.ln, cur.lw);     // util_getPatch (utilities.cpp:55-113), unfused
               if (pnorm) {                           // utilities.cpp:111-112, Eigen's order
                 const float mn = x8_patch_sum(pn.x, pn.y) / N;
                 pn.x = pn.x - mn;
@@ -343,7 +391,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
             const float2 R = s_ref2[i * 32 + lane], GX = s_gx2[i * 32 + lane], GY = s_gy2[i * 32 + lane];
             float ab[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) ab[k] = s_AB[i * 12 + k];
+            for (int k = 0; k < 12; ++k) ab[k] = s_AB[(i / TPP) * 12 + k];
             float sd0[6], sd1[6];
             kx_sd(GX.x, GY.x, ab, sd0);
             kx_sd(GX.y, GY.y, ab, sd1);
@@ -371,7 +419,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
             mbar_wait(&S.full[h], (ground >> 1) & 1);
           }
           const long long tq = trace ? clock64() : 0;
-          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, P, sx, sy);
+          x8_consume_round<NP>(s_ring + h * NP * X8_TILE, lane, j, Q, sx, sy);
           if (trace) tcons += clock64() - tq;
           mbar_arrive(&S.empty[h]);
           ++ground;
@@ -435,7 +483,7 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
 
   if (state) {   // the last iteration ended with a CTA barrier: the arrays are quiescent
     float2* st2 = reinterpret_cast<float2*>(state);
-    for (int e = tid; e < 3 * 32 * P; e += nt) st2[e] = s_ref2[e];
+    for (int e = tid; e < 3 * 32 * Q; e += nt) st2[e] = s_ref2[e];
     for (int e = tid; e < 12 * P; e += nt) state[3 * 64 * P + e] = s_AB[e];
   }
   if (chainw && lane == 0) {
@@ -451,37 +499,47 @@ __global__ void __launch_bounds__((NP + 1) * 32, NP == 7 ? 2 : 1) k_track_x8(con
   }
 }
 
+static int x8_tpp(const ict_optparam& op) { return op.psz == 16 ? 4 : 1; }   // tiles (64 pixels) per patch
 static size_t kx8_smem_np(const ict_optparam& op, int max_pts, int np) {
-  const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack);
-  return sizeof(float) * (3 * 64 * P + 2 * np * X8_TILE + 36 * P);
+  const size_t P = (size_t)(max_pts < op.maxpttrack ? max_pts : op.maxpttrack), Q = P * x8_tpp(op);
+  return sizeof(float) * (3 * 64 * Q + 2 * np * X8_TILE + 36 * P);
 }
-size_t kx8_smem_bytes(const ict_optparam& op, int max_pts) { return kx8_smem_np(op, max_pts, KX_PROD); }
-
-bool kx8_supported(const ict_optparam& op, int max_pts) {
+static bool x8_form_ok(const ict_optparam& op, int max_pts, int np) {
   const int P = max_pts < op.maxpttrack ? max_pts : op.maxpttrack;
-  return op.psz == 8 && P <= KX_PROD * X8_MAXR && kx8_smem_bytes(op, max_pts) <= (size_t)ICT_TRACK_SMEM_LIMIT;
+  return P * x8_tpp(op) <= np * X8_MAXR && kx8_smem_np(op, max_pts, np) <= (size_t)ICT_TRACK_SMEM_LIMIT;
+}
+size_t kx8_smem_bytes(const ict_optparam& op, int max_pts) {
+  return kx8_smem_np(op, max_pts, x8_form_ok(op, max_pts, KX_PROD) ? KX_PROD : 15);
 }
 
-template <bool PN, int NP>
+// 8x8 patches with or without dopatchnorm; 16x16 patches (four tiles per patch) without
+bool kx8_supported(const ict_optparam& op, int max_pts) {
+  if (!(op.psz == 8 || (op.psz == 16 && !op.dopatchnorm))) return false;
+  return x8_form_ok(op, max_pts, KX_PROD) || x8_form_ok(op, max_pts, 15);
+}
+
+template <bool PN, int NP, int TPP>
 static cudaError_t launch_x8_t(const TrackParams& prm, size_t smem, cudaStream_t stream) {
   static bool attr_dev[64] = {};            // function attributes are per device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   bool& attr_set = attr_dev[dev_ & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_track_x8<PN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x8<PN, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(k_track_x8<PN, NP, TPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICT_TRACK_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_track_x8<PN, NP, TPP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_track_x8<PN, NP><<<prm.T, (NP + 1) * 32, smem, stream>>>(prm);
+  k_track_x8<PN, NP, TPP><<<prm.T, (NP + 1) * 32, smem, stream>>>(prm);
   count_launch_external();
   return cudaGetLastError();
 }
 
 cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t stream) {
   if (prm.T <= 0) return cudaSuccess;
+  if (!kx8_supported(prm.op, max_pts)) return cudaErrorInvalidConfiguration;
   const size_t smem7 = kx8_smem_np(prm.op, max_pts, 7), smem15 = kx8_smem_np(prm.op, max_pts, 15);
+  const bool ok7 = x8_form_ok(prm.op, max_pts, 7), ok15 = x8_form_ok(prm.op, max_pts, 15);
   int sms = 148;
   {
     int dev_ = 0;
@@ -490,9 +548,11 @@ cudaError_t launch_track_x8(const TrackParams& prm, int max_pts, cudaStream_t st
   }
   // 15 producers where they cost no residency: one CTA per SM anyway (more than 113 KB with 7), or a batch that does not
   // fill the SMs twice
-  const bool wide = smem15 <= (size_t)ICT_TRACK_SMEM_LIMIT && (2 * (smem7 + 1024) > 228 * 1024 || prm.T <= sms);
-  if (wide) return prm.op.dopatchnorm ? launch_x8_t<true, 15>(prm, smem15, stream) : launch_x8_t<false, 15>(prm, smem15, stream);
-  return prm.op.dopatchnorm ? launch_x8_t<true, 7>(prm, smem7, stream) : launch_x8_t<false, 7>(prm, smem7, stream);
+  const bool wide = ok15 && (!ok7 || 2 * (smem7 + 1024) > 228 * 1024 || prm.T <= sms);
+  if (prm.op.psz == 16)
+    return wide ? launch_x8_t<false, 15, 4>(prm, smem15, stream) : launch_x8_t<false, 7, 4>(prm, smem7, stream);
+  if (wide) return prm.op.dopatchnorm ? launch_x8_t<true, 15, 1>(prm, smem15, stream) : launch_x8_t<false, 15, 1>(prm, smem15, stream);
+  return prm.op.dopatchnorm ? launch_x8_t<true, 7, 1>(prm, smem7, stream) : launch_x8_t<false, 7, 1>(prm, smem7, stream);
 }
 
 }  // namespace ict

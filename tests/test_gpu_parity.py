@@ -717,3 +717,17 @@ def test_psz8_reference_order_both_launch_forms(ict, orc, kw):
     sub["pts"] = case["pts"][:3 * int(case["pt_off"][9])]      # per track: X block, Y block, Z block
     gs = gpu_run(ict, sub, trace_cap=48, sum_order=1)
     assert np.array_equal(gs["p_out"], g["p_out"][:9]) and np.array_equal(gs["iters"], g["iters"][:9])
+
+
+@pytest.mark.parametrize("kw", [dict(npts=20, ntracks=170), dict(npts=50, ntracks=6), dict(npts=1, ntracks=3),
+                                dict(npts=33, ntracks=5, donorm=1, lv_f=2, lv_l=1, maxiter=4, ratio=0.1),
+                                dict(npts=40, maxpttrack=25, ntracks=4), dict(npts=30, scale=3.0, ntracks=8)])
+def test_psz16_reference_order_kernel(ict, orc, kw):
+    """16x16 patches in the reference order run K2x8 with four 64-pixel tiles per patch (both launch forms): bit-identical
+    to the oracle — every iteration's J^T r and delta_p, counts, poses — incl. one point (rank-deficient H), the
+    maxpttrack cap, donorm with lv_l > 0 and large motion (points leaving the frame)."""
+    case = make_case(seed=321, psz=16, w=960, h=544, **kw)
+    o = oracle_run(orc, case, trace_cap=48)
+    g = gpu_run(ict, case, trace_cap=48, sum_order=1)
+    assert np.array_equal(g["pt2d"], o["pt2d"])
+    assert_bit_identical(g, o)
