@@ -470,6 +470,12 @@ struct ict_tracker {
   const int *big_rf = nullptr, *big_nf = nullptr;   // set by ict_track_batch around run_tracks: per-track frames (host) of the multi-CTA path
   DevBuf pt_off, pts, pt3d, norm, p_in, p_out, iters, npix, trace, pt2d, rf, nf, big, teacher, state;
   int teacher_cap = 0;           // ict_tracker_set_teacher: records per track of the staged teacher poses (0: none)
+  // several multi-CTA tracks in one call run on up to ICT_BIG_LANES streams side by side (each track is a chain of a few
+  // hundred small launches: their latencies overlap); every lane has its own work buffer
+  static const int ICT_BIG_LANES = 4;
+  cudaStream_t big_st[ICT_BIG_LANES] = {};
+  cudaEvent_t big_ev[ICT_BIG_LANES + 1] = {};
+  DevBuf big_lane[ICT_BIG_LANES];
   CopyLane lane;      // points (ict_tracker_set_points_stream)
   CopyLane lane_in;   // per-call inputs of ict_track_batch_stream: frame indices, initial poses
 };
@@ -499,6 +505,12 @@ void ict_tracker_destroy(ict_tracker* tr) {
   DevBuf* b[] = {&tr->pt_off, &tr->pts, &tr->pt3d, &tr->norm, &tr->p_in, &tr->p_out, &tr->iters,
                  &tr->npix, &tr->trace, &tr->pt2d, &tr->rf, &tr->nf, &tr->big, &tr->teacher, &tr->state};
   for (DevBuf* x : b) x->release();
+  for (int k = 0; k < ict_tracker::ICT_BIG_LANES; ++k) {
+    tr->big_lane[k].release();
+    if (tr->big_st[k]) cudaStreamDestroy(tr->big_st[k]);
+  }
+  for (int k = 0; k <= ict_tracker::ICT_BIG_LANES; ++k)
+    if (tr->big_ev[k]) cudaEventDestroy(tr->big_ev[k]);
   tr->lane.release();
   tr->lane_in.release();
   delete tr;
@@ -697,16 +709,40 @@ static int run_tracks(ict_tracker* tr, const ict_frames* fs, const int* rf_dev, 
     // tracks too large for one CTA's shared memory: multi-CTA path, one track at a time
     if (tr->h_off.empty()) return fail(ICT_ERR_UNSUPPORTED, "big tracks need host-side pt_off (use ict_tracker_set_points)");
     if (rf_dev) return fail(ICT_ERR_UNSUPPORTED, "big tracks take fixed ref/new frames (use ict_track_sequence or T=1)");
-    size_t wb = 0;                          // one work buffer, sized for the largest track, reused in stream order
+    size_t wb = 0;                          // work buffers sized for the largest track, reused in stream order
     for (int t = 0; t < tr->T; ++t) {
       const size_t w = bigtrack_work_bytes(tr->op, tr->h_off[t + 1] - tr->h_off[t]);
       wb = w > wb ? w : wb;
     }
-    CU(tr->big.reserve(wb));
-    for (int t = 0; t < tr->T; ++t) {
-      const int64_t n = tr->h_off[t + 1] - tr->h_off[t];
-      if (tr->big_rf) { prm.fixed_ref = tr->big_rf[t]; prm.fixed_new = tr->big_nf[t]; }
-      CU(launch_track_big(prm, t, n, tr->big.p, st));
+    // lanes: as many as there are tracks, at most ICT_BIG_LANES, and only while their work buffers stay below 2 GB
+    int nl = tr->T < ict_tracker::ICT_BIG_LANES ? tr->T : ict_tracker::ICT_BIG_LANES;
+    while (nl > 1 && wb * (size_t)nl > ((size_t)2 << 30)) --nl;
+    if (nl <= 1) {
+      CU(tr->big.reserve(wb));
+      for (int t = 0; t < tr->T; ++t) {
+        const int64_t n = tr->h_off[t + 1] - tr->h_off[t];
+        if (tr->big_rf) { prm.fixed_ref = tr->big_rf[t]; prm.fixed_new = tr->big_nf[t]; }
+        CU(launch_track_big(prm, t, n, tr->big.p, st));
+      }
+    } else {
+      for (int k = 0; k < nl; ++k) {
+        if (!tr->big_st[k]) CU(cudaStreamCreateWithFlags(&tr->big_st[k], cudaStreamNonBlocking));
+        CU(tr->big_lane[k].reserve(wb));
+      }
+      for (int k = 0; k <= nl; ++k)
+        if (!tr->big_ev[k]) CU(cudaEventCreateWithFlags(&tr->big_ev[k], cudaEventDisableTiming));
+      CU(cudaEventRecord(tr->big_ev[nl], st));                 // the lanes start after what is already on the caller's stream
+      for (int k = 0; k < nl; ++k) CU(cudaStreamWaitEvent(tr->big_st[k], tr->big_ev[nl], 0));
+      for (int t = 0; t < tr->T; ++t) {
+        const int k = t % nl;
+        const int64_t n = tr->h_off[t + 1] - tr->h_off[t];
+        if (tr->big_rf) { prm.fixed_ref = tr->big_rf[t]; prm.fixed_new = tr->big_nf[t]; }
+        CU(launch_track_big(prm, t, n, tr->big_lane[k].p, tr->big_st[k]));
+      }
+      for (int k = 0; k < nl; ++k) {                            // ... and the caller's stream continues after all of them
+        CU(cudaEventRecord(tr->big_ev[k], tr->big_st[k]));
+        CU(cudaStreamWaitEvent(st, tr->big_ev[k], 0));
+      }
     }
   }
   tr->have_2d = true;
