@@ -389,6 +389,33 @@ __global__ void __launch_bounds__(256) k_big_iter_elems(const BigArgs a, int sl)
   cta_partials<6>(acc, a.w.part);
 }
 
+// solve, pose update, stop rule and trace record of one iteration (one thread); sum6 = the six sums of J^T r
+__device__ __forceinline__ void big_iter_finish_serial(const BigArgs& a, int sl, const float* sum6) {
+  BigState* S = a.w.st;
+  const ict_optparam& op = a.prm.op;
+  float sumsd[6], dp[6];
+  for (int k = 0; k < 6; ++k) sumsd[k] = sum6[k];
+  lu6_solve(S->lu, sumsd, dp);
+  for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
+  se3_exp<float>(S->G, S->p);
+  const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
+  if (S->it == 0) S->normdp_init = normdp;
+  S->normdp = normdp;
+  if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
+    float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
+    rec[0] = (float)sl;
+    rec[1] = (float)S->it;
+    for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
+    rec[14] = normdp;
+    rec[15] = (float)S->nvis;
+    for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
+  }
+  S->npix += (long long)S->nvis * op.novals;
+  S->nvis = 0;
+  S->it += 1;
+  S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
+}
+
 __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl, int ncta) {
   BigState* S = a.w.st;
   if (!S->cont) return;
@@ -399,30 +426,7 @@ __global__ void __launch_bounds__(256) k_big_iter_finish(const BigArgs a, int sl
   } else {
     finish_partials<6>(a.w.part, ncta, s_sum);
   }
-  if (threadIdx.x == 0) {
-    const ict_optparam& op = a.prm.op;
-    float sumsd[6], dp[6];
-    for (int k = 0; k < 6; ++k) sumsd[k] = s_sum[k];
-    lu6_solve(S->lu, sumsd, dp);
-    for (int k = 0; k < 6; ++k) S->p[k] += dp[k];
-    se3_exp<float>(S->G, S->p);
-    const float normdp = ((fabsf(dp[0]) + fabsf(dp[2])) + (fabsf(dp[1]) + fabsf(dp[3]))) + (fabsf(dp[4]) + fabsf(dp[5]));
-    if (S->it == 0) S->normdp_init = normdp;
-    S->normdp = normdp;
-    if (a.prm.trace && S->trace_n < a.prm.trace_cap) {
-      float* rec = a.prm.trace + ((int64_t)a.t * a.prm.trace_cap + S->trace_n++) * ICT_TRACE_FLOATS;
-      rec[0] = (float)sl;
-      rec[1] = (float)S->it;
-      for (int k = 0; k < 6; ++k) { rec[2 + k] = sumsd[k]; rec[8 + k] = dp[k]; }
-      rec[14] = normdp;
-      rec[15] = (float)S->nvis;
-      for (int k = 16; k < ICT_TRACE_FLOATS; ++k) rec[k] = 0.0f;
-    }
-    S->npix += (long long)S->nvis * op.novals;
-    S->nvis = 0;
-    S->it += 1;
-    S->cont = (S->it < op.maxiter) & ((S->normdp / S->normdp_init) > op.normdp_ratio);
-  }
+  if (threadIdx.x == 0) big_iter_finish_serial(a, sl, s_sum);
 }
 
 // ---- reference-order (sum_mode 1) variants -----------------------------------------------------------------------------
@@ -485,6 +489,62 @@ __global__ void __launch_bounds__(256) k_big_products(const BigArgs a, int pass)
       }
     }
   }
+}
+
+// Reference order, no patch normalisation: k_big_iter_points + k_big_iter_pdiff + k_big_products<0> in one launch.  Every
+// element re-derives its point's projection and placement (the same operations on the same operands: the same bits)
+// instead of reading them from per-point arrays written by an earlier launch; the point's first element counts it.
+__global__ void __launch_bounds__(256) k_big_iter_fused_exact(const BigArgs a, int sl) {
+  BigState* S = a.w.st;
+  if (!S->cont) return;
+  const CamLevels& cam = a.prm.cam;
+  const float fx = cam.fx[sl], fy = cam.fy[sl], cx = cam.cx[sl], cy = cam.cy[sl], swo = cam.swo[sl], sho = cam.sho[sl];
+  const int width = cam.width[sl], n = a.prm.op.novals, psz = a.prm.op.psz, pszd2 = a.prm.op.pszd2;
+  const float* __restrict__ Inew = a.prm.frames[a.prm.fixed_new].I[sl];
+  const float* q3 = a.prm.pt3d + 3 * a.prm.pt_off[a.t];
+  const long long lim = a.E;
+  const long long nj = (lim + 7) / 8;
+  const float* cf = a.w.coef;
+  float G[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) G[k] = S->G[k];
+  int cnt = 0;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < nj; j += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const long long e = 8 * j + c;
+      if (e < lim) {
+        const long long i = n == 1 ? e : e / n;
+        const int rem = (int)(e - i * n), r = rem / psz, cc = rem - r * psz;
+        const float X = q3[i], Y = q3[a.n_in + i], Z = q3[2 * (int64_t)a.n_in + i];
+        const float tx = G[0] * X + G[1] * Y + G[2] * Z + G[3];
+        const float ty = G[4] * X + G[5] * Y + G[6] * Z + G[7];
+        const float tz = G[8] * X + G[9] * Y + G[10] * Z + G[11];
+        const float mx = (tx / tz) * fx + cx;
+        const float my = (ty / tz) * fy + cy;
+        const bool vis = (mx >= 0) & (my >= 0) & (mx <= swo) & (my <= sho);
+        float pd = 0.0f;
+        if (vis) {
+          const PatchPlace pp = patch_place(mx, my, pszd2, width);
+          const float pn = bilin4(Inew, pp.base + r * width + cc, width, pp.w0, pp.w1, pp.w2, pp.w3);
+          pd = a.w.ref[e] - pn;
+          if (rem == 0) ++cnt;
+        }
+        const float gx = a.w.gx[e], gy = a.w.gy[e];
+        float sd[6];
+        sd[0] = gx * cf[0 * (long long)a.P + i];
+        sd[1] = gy * cf[1 * (long long)a.P + i];
+        sd[2] = gx * cf[2 * (long long)a.P + i] + gy * cf[3 * (long long)a.P + i];
+        sd[3] = gx * cf[4 * (long long)a.P + i] + gy * cf[5 * (long long)a.P + i];
+        sd[4] = gx * cf[6 * (long long)a.P + i] + gy * cf[7 * (long long)a.P + i];
+        sd[5] = gx * cf[8 * (long long)a.P + i] + gy * cf[9 * (long long)a.P + i];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a.w.prod[big_prod_idx(q, c, j, a.w.cstride)] = sd[q] * pd;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);   // integer count: order-independent
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&S->nvis, cnt);
 }
 
 // One CTA (one warp) per quantity q < nq.  out[q] = the Eigen-order sum of the quantity's E values (zeros up to
@@ -1015,6 +1075,16 @@ cudaError_t launch_track_big(const TrackParams& prm, int t, int64_t npts, void* 
       k_big_level_finish<<<1, 256, 0, st>>>(a, sl); ++nl;
     }
     for (int it = 0; it < op.maxiter; ++it) {
+      if (ex && !pn && a.E <= (1 << 18)) {
+        // three launches per iteration instead of five: products of all elements, the chains, the serial tail.  For
+        // tracks whose launches are latency-bound; beyond ~256 k elements the three streaming kernels below are faster
+        // than the fused one.  (The serial tail inside the chain kernel's last CTA was measured: passing the argument
+        // block on costs the chain kernel a local copy of it, 26 -> 32 ms per dense TrackPose.)
+        k_big_iter_fused_exact<<<ncta, 256, 0, st>>>(a, sl); ++nl;
+        k_big_chains<<<6, 64, chain_smem, st>>>(a, 6, a.w.part, 1); ++nl;
+        k_big_iter_finish<<<1, 256, 0, st>>>(a, sl, 1); ++nl;
+        continue;
+      }
       k_big_iter_points<<<pcta, 256, 0, st>>>(a, sl); ++nl;
       if (pn) {
         k_big_iter_sample<<<ncta, 256, 0, st>>>(a, sl); ++nl;
