@@ -541,7 +541,10 @@ __global__ void __launch_bounds__((NPROD + 2) * 32, NPROD == 4 ? 2 : 1) k_track_
 #pragma unroll
               for (int r = 0; r < 16; ++r) win[r * KR_WROW + perm] = 0.0f;   // sd_proj stays zero (odometer.cpp:352-357)
             }
-            fence_proxy_async();          // the next write to this slot is a TMA (async proxy)
+            // No proxy fence here.  The next write to this slot is a TMA (async proxy), but it is issued by a lane that
+            // first acquires slot_free[u] — released by the chain warps after they have READ these stores — and then
+            // executes fence.proxy.async itself: the stores are ordered before that fence by the release/acquire chain.
+            // A fence.proxy.async per producer lane and unit here sat on the path to every unit's flag: 5 % of the kernel.
             __syncwarp();
             if (lane == 0) st_release_s(&S.pd_flag[u], gi + 1u);
           }
